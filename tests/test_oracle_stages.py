@@ -1,0 +1,258 @@
+"""The C++ oracle against an independent numpy restatement (integer stages, bit-exact) and against
+self-consistency properties (Jacobian vs finite differences of the warp, pose recovery, tracker semantics)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import np_restate as NP
+from vors_b200 import synth
+
+SHAPES = [(48, 64), (37, 53), (2, 2), (3, 7), (64, 33), (480, 640)]
+
+
+def _img(rng, shape, kind):
+    if kind == "noise":
+        return rng.integers(0, 256, shape, dtype=np.uint8)
+    if kind == "const":
+        return np.full(shape, 1, np.uint8)  # benches/mean_pyramid.rs:10
+    if kind == "extreme":
+        return (rng.integers(0, 2, shape) * 255).astype(np.uint8)
+    yy, xx = np.mgrid[0:shape[0], 0:shape[1]]
+    return ((np.sin(xx / 5.0) + np.cos(yy / 7.0)) * 60 + 128).astype(np.uint8)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("kind", ["noise", "const", "extreme", "smooth"])
+def test_mean_pyramid_and_gradients_bit_exact(oracle, shape, kind):
+    rng = np.random.default_rng(hash((shape, kind)) % 2 ** 32)
+    img = _img(rng, shape, kind)
+    for L in (1, 3, 6, 12):
+        pyr = oracle.mean_pyramid(img, L)
+        ref = NP.mean_pyramid(img, L)
+        assert len(pyr) == len(ref) == len(oracle.pyramid_shapes(*shape, L))
+        for a, b in zip(pyr, ref):
+            assert np.array_equal(a, b)
+    pyr = oracle.mean_pyramid(img, 6)
+    if min(pyr[0].shape) >= 2:
+        gx, gy, g2 = oracle.gradients_tracker(pyr)
+        rx, ry, r2 = NP.gradients_tracker(pyr)
+        for l in range(len(pyr)):
+            assert np.array_equal(gx[l], rx[l]) and np.array_equal(gy[l], ry[l]) and np.array_equal(g2[l], r2[l])
+        # squared norm never wraps u16
+        assert max(int(g.max()) for g in g2) <= 65025
+
+
+def test_centered_gradient_truncates_toward_zero(oracle):
+    img = np.zeros((3, 3), np.uint8)
+    img[1, 0], img[1, 2] = 4, 1  # (1 - 4) / 2 = -1 (trunc), floor would give -2
+    img[0, 1], img[2, 1] = 0, 5  # 5 / 2 = 2
+    gx = np.zeros(9, np.int16)
+    gy = np.zeros(9, np.int16)
+    oracle.lib().ref_gradient_centered(np.ascontiguousarray(img.T).reshape(-1), 3, 3, gx, gy)
+    assert gx.reshape(3, 3).T[1, 1] == -1 and gy.reshape(3, 3).T[1, 1] == 2
+    assert np.count_nonzero(gx) == 1 and np.count_nonzero(gy) == 1  # border stays 0
+
+
+@pytest.mark.parametrize("shape", [(48, 64), (37, 53), (96, 130), (480, 640)])
+@pytest.mark.parametrize("thresh", [0, 7, 300])
+def test_coarse_to_fine_bit_exact(oracle, shape, thresh):
+    rng = np.random.default_rng(shape[0] * 1000 + thresh)
+    for kind in ("noise", "smooth", "const"):
+        img = _img(rng, shape, kind)
+        pyr = oracle.mean_pyramid(img, 5)
+        _, _, g2 = oracle.gradients_tracker(pyr)
+        masks = oracle.c2f_select(thresh, g2)
+        ref = NP.c2f_select(thresh, g2)
+        for a, b in zip(masks, ref):
+            assert np.array_equal(a, b)
+        # coarsest all true; every selected parent yields 1 or 2 children; unselected parents none
+        assert masks[-1].all()
+        for l in range(len(masks) - 1):
+            hr, hc = masks[l + 1].shape
+            m = masks[l][:2 * hr, :2 * hc]
+            cnt = m[0::2, 0::2].astype(int) + m[1::2, 0::2] + m[0::2, 1::2] + m[1::2, 1::2]
+            assert np.all((cnt >= 1) & (cnt <= 2) | ~masks[l + 1])
+            assert np.all(cnt[~masks[l + 1]] == 0)
+            assert not masks[l][2 * hr:, :].any() and not masks[l][:, 2 * hc:].any()
+
+
+def test_example_gradient_recipe_differs_from_tracker_recipe(oracle):
+    # squared_norm_direct divides the un-truncated sum by 4
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (24, 32), dtype=np.uint8)
+    out = np.zeros(img.size, np.uint16)
+    oracle.lib().ref_squared_norm_direct(np.ascontiguousarray(img.T).reshape(-1), 24, 32, out)
+    m = img.astype(np.int32)
+    ref = np.zeros(img.shape, np.int32)
+    ref[1:-1, 1:-1] = ((m[1:-1, 2:] - m[1:-1, :-2]) ** 2 + (m[2:, 1:-1] - m[:-2, 1:-1]) ** 2) // 4
+    assert np.array_equal(out.reshape(32, 24).T, ref.astype(np.uint16))
+
+
+def _cfg(oracle, scene, **kw):
+    d = synth.scene_config_kwargs(scene)
+    d.update(kw)
+    return oracle.default_config(**d)
+
+
+@pytest.fixture(scope="module")
+def small_pair():
+    return synth.make_pair(seed=7, rows=120, cols=160, max_v=0.02, max_w=0.01)
+
+
+def test_idepth_pyramid_and_extract_order(oracle, small_pair):
+    scene, f0, f1, _ = small_pair
+    depth = f0[1].copy()
+    depth[10:30, 20:50] = 0  # unknown depth hole
+    cfg = _cfg(oracle, scene, nb_levels=4)
+    kf = oracle.Keyframe(cfg, depth, f0[0])
+    mask0 = kf.mask0()
+    d0, w0 = kf.idepth_map(0)
+    known = mask0 & (depth != 0)
+    assert np.array_equal(~np.isnan(d0), known)
+    assert np.allclose(d0[known], np.float32(5000.0) / depth[known].astype(np.float32), rtol=0, atol=0)
+    assert np.all(w0[known] == np.float32(1e-4))
+    for l in range(1, 4):
+        dl, wl = kf.idepth_map(l)
+        dp, wp = kf.idepth_map(l - 1)
+        hr, hc = dl.shape
+        kids_d = np.stack([dp[0:2 * hr:2, 0:2 * hc:2], dp[1:2 * hr:2, 0:2 * hc:2], dp[0:2 * hr:2, 1:2 * hc:2], dp[1:2 * hr:2, 1:2 * hc:2]])
+        kids_w = np.stack([wp[0:2 * hr:2, 0:2 * hc:2], wp[1:2 * hr:2, 0:2 * hc:2], wp[0:2 * hr:2, 1:2 * hc:2], wp[1:2 * hr:2, 1:2 * hc:2]])
+        assert np.array_equal(~np.isnan(dl), (~np.isnan(kids_d)).any(0))
+        wsum = kids_w.sum(0)
+        mean = np.nansum(kids_d.astype(np.float64) * kids_w, 0) / np.where(wsum > 0, wsum, 1)
+        k = ~np.isnan(dl)
+        assert np.allclose(dl[k], mean[k], rtol=2e-6)
+        assert np.allclose(wl[k], wsum[k], rtol=1e-6)
+    for l in range(4):
+        xy, idepth, jac = kf.points(l)
+        dl, _ = kf.idepth_map(l)
+        # extract_z: column-major scan, (x = col, y = row)
+        cols, rows = np.nonzero(~np.isnan(dl.T))
+        assert np.array_equal(xy[:, 0], cols) and np.array_equal(xy[:, 1], rows)
+        assert np.array_equal(idepth, dl[rows, cols])
+
+
+def test_jacobian_matches_finite_differences_of_warp(oracle, small_pair):
+    """J = grad(T) . d(warp)/d(xi) at xi = 0 (inverse_compositional.rs:313-341): check the geometric part
+    against central differences of lm_optimizer.rs:213-219's warp composed with se3::exp."""
+    scene, f0, _, _ = small_pair
+    cfg = _cfg(oracle, scene, nb_levels=3)
+    kf = oracle.Keyframe(cfg, f0[1], f0[0])
+    k5 = kf.intrinsics(1)
+    xy, idepth, _ = kf.points(1)
+    L = oracle.lib()
+    h = 1e-3
+    rng = np.random.default_rng(0)
+    for p in rng.choice(len(xy), 40, replace=False):
+        x, y, z = float(xy[p, 0]), float(xy[p, 1]), float(idepth[p])
+        Ju = np.zeros(6, np.float32)
+        Jv = np.zeros(6, np.float32)
+        L.ref_warp_jacobian_at(1.0, 0.0, x, y, z, k5, Ju)  # gu = 1, gv = 0 -> du/dxi
+        L.ref_warp_jacobian_at(0.0, 1.0, x, y, z, k5, Jv)
+        fd = np.zeros((2, 6))
+        for a in range(6):
+            xi = np.zeros(6)
+            xi[a] = h
+            uvp = np.zeros(2, np.float32)
+            uvm = np.zeros(2, np.float32)
+            L.ref_warp(C.byref(oracle.se3_exp(xi)), x, y, z, k5, uvp)
+            L.ref_warp(C.byref(oracle.se3_exp(-xi)), x, y, z, k5, uvm)
+            fd[:, a] = (uvp.astype(np.float64) - uvm) / (2 * h)
+        scale = max(1.0, np.abs(fd).max())
+        assert np.allclose(Ju, fd[0], atol=2e-2 * scale), (Ju, fd[0])
+        assert np.allclose(Jv, fd[1], atol=2e-2 * scale), (Jv, fd[1])
+
+
+def test_eval_f32_and_f64_agree_and_gradient_descends(oracle, small_pair):
+    scene, f0, f1, _ = small_pair
+    cfg = _cfg(oracle, scene, nb_levels=3)
+    kf = oracle.Keyframe(cfg, f0[1], f0[0])
+    pyr1 = oracle.mean_pyramid(f1[0], 3)
+    ident = oracle.Pose.identity()
+    for l in range(3):
+        e0, n0, g0, H0 = kf.eval(l, pyr1[l], ident, 0)
+        e1, n1, g1, H1 = kf.eval(l, pyr1[l], ident, 1)
+        assert n0 == n1 and n0 > 0
+        assert np.isclose(e0, e1, rtol=1e-4)
+        assert np.allclose(g0, g1, rtol=1e-3, atol=1e-3 * np.abs(g1).max())
+        assert np.allclose(H0, H1, rtol=1e-3)
+        assert np.allclose(H1, H1.T)
+    # identical image -> (numerically) zero residual: back_project/project round-off moves u,v by ~1e-5 px
+    e, n, g, H = kf.eval(0, f0[0], ident, 0)
+    assert e < 1e-5 and n > 0
+
+
+def test_pair_alignment_recovers_ground_truth(oracle):
+    scene, f0, f1, pose1 = synth.make_pair(seed=1000)
+    cfg = _cfg(oracle, scene, nb_levels=5)
+    tr = oracle.Tracker(cfg, 0.0, f0[1], 0.0, f0[0])
+    st, stats, trace = tr.track(1.0, f1[1], 1.01, f1[0], trace_cap=512)
+    assert st == 0 and stats.status == 0
+    ts, p = tr.current_frame()
+    assert ts == 1.0  # depth timestamp (inverse_compositional.rs:245)
+    ang, dist = oracle.pose_error(p.as_array(), np.concatenate(pose1))
+    assert ang < 2e-3 and dist < 5e-3, (ang, dist)
+    # trace invariants of the LM loop: levels coarse to fine, energy never increases on accepted steps
+    levels = [r.level for r in trace]
+    assert levels == sorted(levels, reverse=True) and levels[0] == 4 and levels[-1] == 0
+    for a, b in zip(trace, trace[1:]):
+        if a.level == b.level and b.accepted:
+            last_acc = [r for r in trace if r.level == a.level and r.iter < b.iter and r.accepted][-1]
+            assert b.energy <= last_acc.energy
+
+
+def test_fixed_iters_runs_exactly_k_rounds(oracle, small_pair):
+    scene, f0, f1, _ = small_pair
+    cfg = _cfg(oracle, scene, nb_levels=3, fixed_iters=10, candidate_mode=1)
+    tr = oracle.Tracker(cfg, 0.0, f0[1], 0.0, f0[0])
+    st, stats, trace = tr.track(1.0, f1[1], 1.0, f1[0], trace_cap=512)
+    assert st == 0
+    assert list(stats.n_iters)[:3] == [10, 10, 10]
+    assert len(trace) == 3 * 11
+    kf = tr.keyframe()
+    # dense mode: every pixel with depth != 0 is a level-0 candidate
+    assert kf.n_points(0) == int(np.count_nonzero(f0[1]))
+
+
+def test_tracker_keyframe_switch_and_failure_semantics(oracle, small_pair):
+    scene, f0, f1, pose1 = small_pair
+    cfg = _cfg(oracle, scene, nb_levels=3, keyframe_flow_threshold=1e-3)
+    tr = oracle.Tracker(cfg, 0.0, f0[1], 0.0, f0[0])
+    st, stats, _ = tr.track(1.0, f1[1], 1.0, f1[0])
+    assert st == 0 and stats.keyframe_changed == 1
+    _, cur = tr.current_frame()
+    assert np.array_equal(tr.keyframe_pose().as_array(), cur.as_array())  # inverse_compositional.rs:238
+    # all-unknown depth at init -> no candidates -> NaN energy -> zero Hessian -> Cholesky fails;
+    # pose is kept, timestamp still advances (inverse_compositional.rs:191-208)
+    tr2 = oracle.Tracker(cfg, 0.0, np.zeros_like(f0[1]), 0.0, f0[0])
+    st, stats, _ = tr2.track(2.0, f1[1], 2.0, f1[0])
+    assert st == 1 and stats.status == 1
+    ts, p = tr2.current_frame()
+    assert ts == 2.0 and np.array_equal(p.as_array(), np.array([0, 0, 0, 0, 0, 0, 1], np.float32))
+    assert stats.keyframe_changed == 0  # optical flow is NaN, `NaN >= thresh` is false
+
+
+def test_short_pyramid_is_rejected(oracle):
+    scene = synth.make_scene(0, 16, 16)
+    cfg = _cfg(oracle, scene, nb_levels=6)
+    with pytest.raises(ValueError):
+        oracle.Tracker(cfg, 0.0, np.ones((16, 16), np.uint16), 0.0, np.zeros((16, 16), np.uint8))
+
+
+def test_dso_select_deterministic_branches(oracle):
+    rng = np.random.default_rng(11)
+    scene = synth.make_scene(3, 240, 320)
+    gray, _ = synth.render(scene)
+    g2 = np.zeros(gray.size, np.uint16)
+    oracle.lib().ref_squared_norm_direct(np.ascontiguousarray(gray.T).reshape(-1), 240, 320, g2)
+    mag = np.sqrt(g2.astype(np.float32)).astype(np.uint16)
+    mask = np.zeros(gray.size, np.uint8)
+    used = C.c_int()
+    n = oracle.lib().ref_dso_select(mag, 240, 320, 500, 2, 1, mask, C.byref(used))
+    assert n > 0 and 0 < mask.sum() <= n
+    mask2 = np.zeros(gray.size, np.uint8)
+    oracle.lib().ref_dso_select(mag, 240, 320, 500, 2, 1, mask2, C.byref(used))
+    assert np.array_equal(mask, mask2)
+    m = mask.reshape(320, 240).T.astype(bool)
+    assert m.sum() > 0 and np.all(mag.reshape(320, 240).T[m] > 0)
