@@ -1,0 +1,382 @@
+// align_kernel.cu — the persistent direct-alignment kernel, sm_100a.
+//
+// One launch runs COMPLETE alignments: for every job (keyframe, frame, prior) a team of `team` CTAs
+// walks the pyramid coarse to fine and, per level, runs the reference's Levenberg-Marquardt loop
+// (src/math/optimizer.rs:57-70 + src/core/track/lm_optimizer.rs:113-192) entirely on the device:
+//
+//   pass      every thread streams its share of the level's candidates (12 B each, coalesced), warps
+//             them with the folded 3x4 matrix of lie.cuh (lm_optimizer.rs:213-219), tests the
+//             reference's conservative inside rule and samples the current image bilinearly from u8
+//             texels in f32 (lm_optimizer.rs:227-251), forms the residual against the template
+//             value, recomputes the Jacobian (inverse_compositional.rs:313-341) and accumulates
+//             sum r^2, n_inside, g = sum J r and the 21 unique entries of H = sum J J^T in registers
+//             (eval_energy + compute_eval_data, lm_optimizer.rs:68-107, fused and speculative);
+//   reduce    warp shuffles -> shared memory -> f64 per-CTA partials -> (team > 1) peer partials
+//             through global memory with one counter barrier per pass; fixed order => deterministic;
+//   decide    thread 0 of every CTA redundantly replays accept / reject / stop (lm_optimizer.rs:
+//             140-192), damps, solves the 6x6 system by Cholesky, applies se3::exp and the first
+//             order renormalisation (lm_optimizer.rs:123-136, 198-209) and publishes the next
+//             candidate model's warp matrix; no host round trip anywhere in the loop.
+//
+// team == 1 is the throughput configuration (one alignment per CTA, two CTAs per SM so one CTA's
+// serial solve overlaps the other's pass); team > 1 trades efficiency for latency on few streams.
+// No tensor cores: 29 accumulators per candidate, bounded by the fp32 pipe and memory latency.
+#include <cooperative_groups.h>
+
+#include "vors_device.cuh"
+
+namespace vors {
+
+namespace {
+
+constexpr int kBlock = 256;
+constexpr int kWarps = kBlock / 32;
+
+struct LmShared {
+    float M[12];
+    // kept state = last accepted evaluation (lm_optimizer.rs:31-40 `EvalData`)
+    float keptH[21];
+    float keptg[6];
+    float keptE;
+    Pose kept_model;
+    Pose cand_model;
+    Pose out_model;  // lm_model of Tracker::track: result of the last successful level
+    float lam;
+    int iter;
+    int init_phase;
+    int cont;
+    int failed;
+    int n_passes;
+    int trace_len;
+    unsigned long long point_passes;
+    float warp_part[kWarps][32];
+    double tot[32];
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// index of (a, b), a <= b, in the packed upper triangle
+__device__ __host__ constexpr int tri(int a, int b) { return a * 6 - a * (a - 1) / 2 + (b - a); }
+
+struct Acc {
+    float e, n;
+    float g[6];
+    float h[21];
+};
+
+// One candidate: warp, inside test, bilinear sample, residual, Jacobian, accumulate.
+__device__ __forceinline__ void eval_point(uint32_t pk, float rho, uint32_t gr, const float (&M)[12], const Intrinsics& k,
+                                           const uint8_t* __restrict__ img, int rows, float wm2, float hm2, Acc& acc) {
+    const float x = float(pk & 0xFFFu), y = float((pk >> 12) & 0xFFFu);
+    const float U = fmaf(M[0], x, fmaf(M[1], y, fmaf(M[3], rho, M[2])));
+    const float V = fmaf(M[4], x, fmaf(M[5], y, fmaf(M[7], rho, M[6])));
+    const float W = fmaf(M[8], x, fmaf(M[9], y, fmaf(M[11], rho, M[10])));
+    const float iw = __frcp_rn(W);
+    const float u = U * iw, v = V * iw;
+    const float u0 = floorf(u), v0 = floorf(v);
+    // lm_optimizer.rs:231: inside iff 0 <= floor(u) < W-2 and 0 <= floor(v) < H-2 (NaN fails)
+    if (u0 >= 0.0f && u0 < wm2 && v0 >= 0.0f && v0 < hm2) {
+        const uint8_t* p = img + size_t(int(u0)) * rows + int(v0);
+        const float i00 = float(__ldg(p)), i10 = float(__ldg(p + 1));
+        const float i01 = float(__ldg(p + rows)), i11 = float(__ldg(p + rows + 1));
+        const float a = u - u0, b = v - v0;
+        const float val = (1.0f - b) * (1.0f - a) * i00 + b * (1.0f - a) * i10 + (1.0f - b) * a * i01 + b * a * i11;
+        const float r = val - float(pk >> 24);
+        float J[6];
+        jacobian_at(float(int16_t(gr & 0xFFFFu)), float(int16_t(gr >> 16)), x, y, rho, k, J);
+        acc.e = fmaf(r, r, acc.e);
+        acc.n += 1.0f;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc.g[c] = fmaf(J[c], r, acc.g[c]);
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+#pragma unroll
+            for (int d = c; d < 6; ++d) acc.h[tri(c, d)] = fmaf(J[c], J[d], acc.h[tri(c, d)]);
+    }
+}
+
+// The serial part of one LM round, run by thread 0 of every CTA of the team on identical inputs.
+// Mirrors init / eval / stop_criterion / step of lm_optimizer.rs:113-192.
+__device__ __noinline__ void lm_decide(LmShared& S, const AlignParams& P, const AlignJob& job, int job_idx, int lvl, bool writer) {
+    const double* tot = S.tot;
+    const int n_inside = int(tot[1]);
+    // energy = energy_sum / residuals.len() as f32 (lm_optimizer.rs:85); 0/0 = NaN when nothing is inside
+    const float E = float(tot[0]) / float(n_inside);
+    S.n_passes += 1;
+    bool stop;
+    bool accepted = true;
+    const float lam_used = S.init_phase ? P.lm_coef_init : S.lam;
+    if (S.init_phase) {
+        S.lam = P.lm_coef_init;
+        S.iter = 0;
+        S.init_phase = 0;
+        stop = false;
+    } else {
+        const bool rejected = E > S.keptE;  // lm_optimizer.rs:144 (NaN compares false -> accepted)
+        accepted = !rejected;
+        const bool too_many = P.fixed_iters ? (S.iter >= P.fixed_iters) : (S.iter > P.max_iters);
+        if (rejected) {
+            stop = too_many;
+            if (!too_many) S.lam *= P.lm_coef_reject_mult;
+        } else if (too_many) {
+            stop = true;
+        } else {
+            const float d_energy = S.keptE - E;
+            stop = P.fixed_iters ? false : !(d_energy > P.energy_delta_stop);
+            S.lam = P.lm_coef_accept_mult * S.lam;
+        }
+    }
+    if (writer && P.trace && S.trace_len < kTraceCap) {
+        vors_trace_rec& t = P.trace[size_t(job_idx) * kTraceCap + S.trace_len];
+        t.level = lvl;
+        t.iter = S.iter;
+        t.energy = E;
+        t.n_inside = n_inside;
+        t.lm_coef = lam_used;
+        t.accepted = accepted ? 1 : 0;
+    }
+    S.trace_len += 1;
+    if (accepted) {
+        S.keptE = E;
+        for (int c = 0; c < 6; ++c) S.keptg[c] = float(tot[2 + c]);
+        for (int c = 0; c < 21; ++c) S.keptH[c] = float(tot[8 + c]);
+        S.kept_model = S.cand_model;
+    }
+    if (stop) {
+        S.cont = 0;
+        return;
+    }
+    // step (lm_optimizer.rs:123-136)
+    S.iter += 1;
+    float A[36], b[6];
+    for (int r = 0; r < 6; ++r)
+        for (int c = 0; c < 6; ++c) A[r * 6 + c] = S.keptH[r <= c ? tri(r, c) : tri(c, r)];
+    for (int c = 0; c < 6; ++c) A[c * 6 + c] *= 1.0f + S.lam;
+    for (int c = 0; c < 6; ++c) b[c] = S.keptg[c];
+    if (!cholesky6_solve(A, b)) {
+        S.failed = 1;
+        S.cont = 0;
+        return;
+    }
+    const Pose delta = se3_exp(b);
+    S.cand_model = pose_renormalize(pose_mul(S.kept_model, pose_inverse(delta)));
+    warp_matrix(S.cand_model, job.lv[lvl].k, S.M);
+    S.cont = 1;
+}
+
+__global__ void __launch_bounds__(kBlock, 2) k_align(const AlignParams P) {
+    __shared__ LmShared S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int team = P.team;
+    const int team_id = blockIdx.x / team, rank = blockIdx.x - team_id * team;
+    const int n_teams = gridDim.x / team;
+    TeamScratch* scratch = team > 1 ? P.scratch + team_id : nullptr;
+    unsigned epoch = 0;  // passes this team has synchronised on so far (same in every CTA of the team)
+
+    for (int job_idx = team_id; job_idx < P.n_jobs; job_idx += n_teams) {
+        const AlignJob& job = P.jobs[job_idx];
+        const bool writer = (rank == 0);
+        if (tid == 0) {
+            S.out_model = P.init[job_idx];
+            S.failed = 0;
+            S.n_passes = 0;
+            S.trace_len = 0;
+            S.point_passes = 0ull;
+        }
+        __syncthreads();
+
+        for (int lvl = job.lvl_first; lvl >= job.lvl_last; --lvl) {
+            const LevelJob& lj = job.lv[lvl];
+            const int n = *lj.n_ptr;
+            const int rows = lj.rows;
+            const float wm2 = float(lj.cols - 2), hm2 = float(rows - 2);
+            const Intrinsics k = lj.k;
+            const uint32_t* __restrict__ pk = lj.pk;
+            const float* __restrict__ idp = lj.idepth;
+            const uint32_t* __restrict__ grd = lj.grad;
+            const uint8_t* __restrict__ img = lj.img;
+            if (tid == 0) {
+                S.cand_model = S.out_model;
+                S.init_phase = 1;
+                warp_matrix(S.cand_model, k, S.M);
+            }
+            __syncthreads();
+
+            for (;;) {
+                float M[12];
+#pragma unroll
+                for (int c = 0; c < 12; ++c) M[c] = S.M[c];
+                Acc acc;
+                acc.e = 0.0f;
+                acc.n = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) acc.g[c] = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 21; ++c) acc.h[c] = 0.0f;
+
+                // ---- pass: candidates interleaved over the team's threads (coalesced 4-byte streams)
+                const int stride = team * kBlock;
+#pragma unroll 2
+                for (int i = rank * kBlock + tid; i < n; i += stride) eval_point(pk[i], idp[i], grd[i], M, k, img, rows, wm2, hm2, acc);
+
+                // ---- reduce: warp shuffle, then per-CTA f64 sums in fixed order
+                float vals[kNumAcc];
+                vals[0] = acc.e;
+                vals[1] = acc.n;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) vals[2 + c] = acc.g[c];
+#pragma unroll
+                for (int c = 0; c < 21; ++c) vals[8 + c] = acc.h[c];
+#pragma unroll
+                for (int c = 0; c < kNumAcc; ++c) {
+                    float v = vals[c];
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                    vals[c] = v;
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int c = 0; c < kNumAcc; ++c) S.warp_part[warp][c] = vals[c];
+                }
+                __syncthreads();
+                if (tid < kNumAcc) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int w = 0; w < kWarps; ++w) s += double(S.warp_part[w][tid]);
+                    if (team > 1) {
+                        scratch->part[epoch & 1][rank][tid] = s;
+                        __threadfence();
+                    } else {
+                        S.tot[tid] = s;
+                    }
+                }
+                if (team > 1) {
+                    __syncthreads();
+                    ++epoch;
+                    if (tid == 0) {
+                        atomicAdd(&scratch->counter, 1u);
+                        const unsigned target = epoch * unsigned(team);
+                        while (ld_acquire_u32(&scratch->counter) < target) __nanosleep(32);
+                    }
+                    __syncthreads();
+                    if (tid < kNumAcc) {
+                        double s = 0.0;
+                        const double* pp = &scratch->part[(epoch - 1) & 1][0][tid];
+                        for (int r = 0; r < team; ++r) s += __ldcg(pp + r * 32);
+                        S.tot[tid] = s;
+                    }
+                }
+                __syncthreads();
+
+                // ---- decide + step (serial, redundantly identical in every CTA of the team)
+                if (tid == 0) {
+                    S.point_passes += (unsigned long long)n;
+                    if (job.pass_only) {
+                        S.n_passes += 1;
+                        S.cont = 0;
+                    } else {
+                        lm_decide(S, P, job, job_idx, lvl, writer);
+                    }
+                }
+                __syncthreads();
+                if (!S.cont) break;
+            }
+
+            if (job.pass_only) {
+                if (writer && tid == 0) {
+                    AlignResult& R = P.results[job_idx];
+                    R.pass_n_inside = int(S.tot[1]);
+                    R.pass_energy = float(S.tot[0]) / float(int(S.tot[1]));
+                    for (int c = 0; c < 6; ++c) R.pass_g[c] = float(S.tot[2 + c]);
+                    for (int c = 0; c < 21; ++c) R.pass_H[c] = float(S.tot[8 + c]);
+                }
+                break;
+            }
+            if (writer && tid == 0) {
+                AlignResult& R = P.results[job_idx];
+                R.n_iters[lvl] = S.iter;
+                R.energy[lvl] = S.keptE;
+                R.n_points[lvl] = n;
+            }
+            const int failed = S.failed;
+            if (tid == 0 && !failed) S.out_model = S.kept_model;  // inverse_compositional.rs:193
+            __syncthreads();
+            if (failed) break;  // inverse_compositional.rs:195-199
+        }
+
+        // ---- optical flow of the coarsest level's candidates under lm_model (inverse_compositional.rs:210-221)
+        float flow = 0.0f;
+        if (job.flow_level >= 0 && !job.pass_only) {
+            const LevelJob& lj = job.lv[job.flow_level];
+            const int n = *lj.n_ptr;
+            if (tid == 0) warp_matrix(S.out_model, lj.k, S.M);
+            __syncthreads();
+            float s = 0.0f;
+            if (rank == 0) {
+                for (int i = tid; i < n; i += kBlock) {
+                    const uint32_t p = lj.pk[i];
+                    const float rho = lj.idepth[i];
+                    const float x = float(p & 0xFFFu), y = float((p >> 12) & 0xFFFu);
+                    const float U = fmaf(S.M[0], x, fmaf(S.M[1], y, fmaf(S.M[3], rho, S.M[2])));
+                    const float V = fmaf(S.M[4], x, fmaf(S.M[5], y, fmaf(S.M[7], rho, S.M[6])));
+                    const float W = fmaf(S.M[8], x, fmaf(S.M[9], y, fmaf(S.M[11], rho, S.M[10])));
+                    s += fabsf(x - U / W) + fabsf(y - V / W);
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+                if (lane == 0) S.warp_part[warp][0] = s;
+            }
+            __syncthreads();
+            if (rank == 0 && tid == 0) {
+                double t = 0.0;
+                for (int w = 0; w < kWarps; ++w) t += double(S.warp_part[w][0]);
+                flow = float(t) / float(n);  // 0/0 = NaN with no candidates, like the reference
+            }
+        }
+        if (writer && tid == 0) {
+            AlignResult& R = P.results[job_idx];
+            R.model = S.out_model;
+            R.status = S.failed ? VORS_OPTIMIZATION_FAILED : VORS_OK;
+            R.optical_flow = flow;
+            R.n_passes = S.n_passes;
+            R.trace_len = S.trace_len < kTraceCap ? S.trace_len : kTraceCap;
+            R.point_passes = S.point_passes;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+cudaError_t align_query(AlignLaunchInfo* info) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    int sms = 0, per_sm = 0;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align, kBlock, 0);
+    if (e != cudaSuccess) return e;
+    info->block = kBlock;
+    info->sm_count = sms;
+    info->max_resident_ctas = sms * per_sm;
+    return cudaSuccess;
+}
+
+cudaError_t launch_align(Launcher& L, const AlignParams& p, int n_teams) {
+    const int grid = n_teams * p.team;
+    ++L.launches;
+    if (p.team > 1) {
+        // co-residency of a team's CTAs is required by the counter barrier: cooperative launch checks it
+        void* args[] = {(void*)&p};
+        return cudaLaunchCooperativeKernel((const void*)k_align, dim3(grid), dim3(kBlock), args, 0, L.stream);
+    }
+    k_align<<<grid, kBlock, 0, L.stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace vors

@@ -1,0 +1,415 @@
+// image_kernels.cu — keyframe / frame precompute kernels, sm_100a.
+//
+// All integer stages are bit-exact restatements of the reference semantics (truncating signed
+// division, u16 wrap of `third + thresh`, stable tie-break of the 4-element sort).  Every kernel
+// is batched over streams through blockIdx.y (`items` maps the launch index to the stream slab).
+#include "vors_device.cuh"
+
+namespace vors {
+
+namespace {
+
+__device__ __forceinline__ int item_of(const int* items, int j) { return items ? items[j] : j; }
+
+// ------------------------------------------------------------------------------------------------
+// Row-major (decoder output) -> column-major (internal, nalgebra) transposition; what
+// `DMatrix::from_row_slice` does on the CPU in the reference (src/misc/interop.rs:53-56).
+template <typename T>
+__global__ void k_transpose(const T* __restrict__ in, T* __restrict__ out_slab, size_t out_stride, const int* __restrict__ items,
+                            int rows, int cols) {
+    __shared__ T tile[32][33];
+    const int j = blockIdx.z;
+    const T* src = in + size_t(j) * rows * cols;
+    T* dst = out_slab + size_t(item_of(items, j)) * out_stride;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        const int r = r0 + dy, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[dy][threadIdx.x] = src[size_t(r) * cols + c];
+    }
+    __syncthreads();
+    for (int dx = threadIdx.y; dx < 32; dx += blockDim.y) {
+        const int c = c0 + dx, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) dst[size_t(c) * rows + r] = tile[threadIdx.x][dx];
+    }
+}
+
+__global__ void k_copy_items_u16(const uint16_t* __restrict__ in, uint16_t* __restrict__ out_slab, size_t out_stride,
+                                 const int* __restrict__ items, size_t count) {
+    const int j = blockIdx.y;
+    const uint16_t* src = in + size_t(j) * count;
+    uint16_t* dst = out_slab + size_t(item_of(items, j)) * out_stride;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += size_t(gridDim.x) * blockDim.x) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row A: one level of `multires::mean_pyramid` (multires.rs:21-31): ((a+b+c+d)/4) as u8 over 2x2
+// blocks a=(2i,2j) b=(2i+1,2j) c=(2i,2j+1) d=(2i+1,2j+1); odd last row/col dropped.
+__global__ void k_halve_mean(const Geom g, int l, uint8_t* __restrict__ pyr_slab, const int* __restrict__ items) {
+    uint8_t* pyr = pyr_slab + size_t(item_of(items, blockIdx.y)) * g.pix_total;
+    const uint8_t* in = pyr + g.off[l - 1];
+    uint8_t* out = pyr + g.off[l];
+    const int R = g.rows[l], C = g.cols[l], Rin = g.rows[l - 1];
+    const int n = R * C;
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
+        const int x = o / R, y = o - x * R;
+        const uint8_t* p = in + size_t(2 * x) * Rin + 2 * y;
+        const unsigned a = p[0], b = p[1], c = p[Rin], d = p[Rin + 1];
+        out[o] = uint8_t((a + b + c + d) >> 2);
+    }
+}
+
+// Rows B, C, D: the Tracker's gradient recipe (inverse_compositional.rs:112-117) for every level in
+// one launch.  Level 0: gradient::centered (gradient.rs:15-33), i16 division truncating toward zero,
+// 1-px border 0.  Level l >= 1: bloc_x / bloc_y of the level l-1 image (gradient.rs:74-93).
+// g2 = (gx*gx + gy*gy) as u16 (gradient.rs:38-44).
+__global__ void k_gradients(const Geom g, const uint8_t* __restrict__ pyr_slab, uint32_t* __restrict__ grad_slab,
+                            uint16_t* __restrict__ g2_slab, const int* __restrict__ items) {
+    const size_t base = size_t(item_of(items, blockIdx.y)) * g.pix_total;
+    const uint8_t* pyr = pyr_slab + base;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.pix_total; i += gridDim.x * blockDim.x) {
+        int l = 0;
+#pragma unroll
+        for (int k = 1; k < kMaxLevels; ++k)
+            if (k < g.L && i >= g.off[k]) l = k;
+        const int o = i - g.off[l];
+        const int R = g.rows[l], C = g.cols[l];
+        const int x = o / R, y = o - x * R;
+        int gx = 0, gy = 0;
+        if (l == 0) {
+            if (x > 0 && x < C - 1 && y > 0 && y < R - 1) {
+                const uint8_t* p = pyr + size_t(x) * R + y;
+                gx = (int(p[R]) - int(p[-R])) / 2;  // right - left, C++ `/` truncates like Rust
+                gy = (int(p[1]) - int(p[-1])) / 2;  // bottom - top
+            }
+        } else {
+            const int Rin = g.rows[l - 1];
+            const uint8_t* p = pyr + g.off[l - 1] + size_t(2 * x) * Rin + 2 * y;
+            const int a = p[0], b = p[1], c = p[Rin], d = p[Rin + 1];
+            gx = (c + d - a - b) / 2;
+            gy = (b - a + d - c) / 2;
+        }
+        if (grad_slab) grad_slab[base + i] = (uint32_t(gx) & 0xFFFFu) | (uint32_t(gy) << 16);
+        if (g2_slab) g2_slab[base + i] = uint16_t(gx * gx + gy * gy);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row E: one level of candidates::coarse_to_fine::select (coarse_to_fine.rs:15-89).  One thread per
+// (ceil) parent of level l+1: a selected parent keeps its max child and, if second > third + thresh
+// (u16 arithmetic), the second max; everything else (unselected parents, odd border) is false.
+// A stable ascending sort of (value, index) pairs is a plain sort of value<<2|index keys.
+__device__ __forceinline__ void cswap(unsigned& a, unsigned& b) {
+    const unsigned lo = min(a, b), hi = max(a, b);
+    a = lo;
+    b = hi;
+}
+
+__global__ void k_c2f_level(const Geom g, int l, uint16_t thresh, const uint16_t* __restrict__ g2_slab,
+                            uint8_t* __restrict__ mask_slab, const int* __restrict__ items) {
+    const size_t base = size_t(item_of(items, blockIdx.y)) * g.pix_total;
+    const uint16_t* g2 = g2_slab + base + g.off[l];
+    uint8_t* mask = mask_slab + base + g.off[l];
+    const uint8_t* pre = (l + 1 == g.L - 1) ? nullptr : mask_slab + base + g.off[l + 1];  // coarsest: all true
+    const int R = g.rows[l], C = g.cols[l], Rp = g.rows[l + 1], Cp = g.cols[l + 1];
+    const int PR = (R + 1) / 2, PC = (C + 1) / 2;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < PR * PC; t += gridDim.x * blockDim.x) {
+        const int px = t / PR, py = t - px * PR;
+        const bool real_parent = (py < Rp) && (px < Cp);
+        uint8_t ok[4] = {0, 0, 0, 0};
+        if (real_parent && (pre == nullptr || pre[size_t(px) * Rp + py])) {
+            const uint16_t* p = g2 + size_t(2 * px) * R + 2 * py;
+            unsigned k0 = (unsigned(p[0]) << 2) | 0u, k1 = (unsigned(p[1]) << 2) | 1u;
+            unsigned k2 = (unsigned(p[R]) << 2) | 2u, k3 = (unsigned(p[R + 1]) << 2) | 3u;
+            cswap(k0, k1); cswap(k2, k3); cswap(k0, k2); cswap(k1, k3); cswap(k1, k2);
+            const unsigned first = k3 & 3u, second = k2 & 3u;
+            const uint16_t x = uint16_t(k2 >> 2), y = uint16_t(k1 >> 2);
+            ok[first] = 1;
+            if (x > uint16_t(y + thresh)) ok[second] = 1;
+        }
+        const int y0 = 2 * py, x0 = 2 * px;
+        if (y0 < R && x0 < C) mask[size_t(x0) * R + y0] = ok[0];
+        if (y0 + 1 < R && x0 < C) mask[size_t(x0) * R + y0 + 1] = ok[1];
+        if (y0 < R && x0 + 1 < C) mask[size_t(x0 + 1) * R + y0] = ok[2];
+        if (y0 + 1 < R && x0 + 1 < C) mask[size_t(x0 + 1) * R + y0 + 1] = ok[3];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row F: helper::zip_mask_map + inverse_depth::from_depth (helper.rs:40-47, inverse_depth.rs:24-29):
+// idepth = depth_scale / depth where mask and depth != 0; Unknown is encoded as NaN (weight 0).
+__global__ void k_idepth0(const Geom g, const uint16_t* __restrict__ depth_slab, size_t depth_stride,
+                          const uint8_t* __restrict__ mask_slab, int dense, float scale, float variance,
+                          float* __restrict__ idepth_slab, float* __restrict__ weight_slab, const int* __restrict__ items) {
+    const int it = item_of(items, blockIdx.y);
+    const size_t base = size_t(it) * g.pix_total;
+    const uint16_t* depth = depth_slab + size_t(it) * depth_stride;
+    const int n = g.rows[0] * g.cols[0];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint16_t d = depth[i];
+        const bool known = (dense || mask_slab[base + i]) && d != 0;
+        idepth_slab[base + i] = known ? scale / float(d) : __int_as_float(0x7fc00000);
+        weight_slab[base + i] = known ? variance : 0.0f;
+    }
+}
+
+// Row G: one halving of the idepth pyramid with inverse_depth::fuse + strategy_dso_mean
+// (inverse_depth.rs:49-98): weighted mean of the known children in (a,b,c,d) order, evaluated left
+// to right in f32; one known child is copied verbatim; none -> Unknown.
+__global__ void k_idepth_halve(const Geom g, int l, float* __restrict__ idepth_slab, float* __restrict__ weight_slab,
+                               const int* __restrict__ items) {
+    const size_t base = size_t(item_of(items, blockIdx.y)) * g.pix_total;
+    const float* din = idepth_slab + base + g.off[l - 1];
+    const float* win = weight_slab + base + g.off[l - 1];
+    float* dout = idepth_slab + base + g.off[l];
+    float* wout = weight_slab + base + g.off[l];
+    const int R = g.rows[l], C = g.cols[l], Rin = g.rows[l - 1];
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < R * C; o += gridDim.x * blockDim.x) {
+        const int x = o / R, y = o - x * R;
+        const size_t p = size_t(2 * x) * Rin + 2 * y;
+        const float dd[4] = {din[p], din[p + 1], din[p + Rin], din[p + Rin + 1]};
+        const float ww[4] = {win[p], win[p + 1], win[p + Rin], win[p + Rin + 1]};
+        float ds[4], vs[4];
+        int n = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (!isnan(dd[k])) {
+                ds[n] = dd[k];
+                vs[n] = ww[k];
+                ++n;
+            }
+        float d = __int_as_float(0x7fc00000), w = 0.0f;
+        // explicit __fmul_rn/__fadd_rn: the reference rounds every product and sum (no FMA contraction)
+        if (n == 1) {
+            d = ds[0];
+            w = vs[0];
+        } else if (n == 2) {
+            w = __fadd_rn(vs[0], vs[1]);
+            d = __fdiv_rn(__fadd_rn(__fmul_rn(ds[0], vs[0]), __fmul_rn(ds[1], vs[1])), w);
+        } else if (n == 3) {
+            w = __fadd_rn(__fadd_rn(vs[0], vs[1]), vs[2]);
+            d = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(ds[0], vs[0]), __fmul_rn(ds[1], vs[1])), __fmul_rn(ds[2], vs[2])), w);
+        } else if (n == 4) {
+            w = __fadd_rn(__fadd_rn(__fadd_rn(vs[0], vs[1]), vs[2]), vs[3]);
+            d = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(ds[0], vs[0]), __fmul_rn(ds[1], vs[1])), __fmul_rn(ds[2], vs[2])),
+                                    __fmul_rn(ds[3], vs[3])),
+                          w);
+        }
+        dout[o] = d;
+        wout[o] = w;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row H: `extract_z` (inverse_compositional.rs:260-279) — ordered stream compaction of the known
+// idepths of every level, in memory (= column-major scan) order.  Three launches for all levels
+// and all streams: per-block counts, per-(stream, level) exclusive scan, ordered scatter.  The
+// scatter also gathers what the align kernel needs per candidate (template value, gradient pair).
+__device__ __forceinline__ int level_of_block(const Geom& g, int blk) {
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < kMaxLevels; ++k)
+        if (k < g.L && blk >= g.blk_off[k]) l = k;
+    return l;
+}
+
+__global__ void __launch_bounds__(kCompactBlock) k_compact_count(const Geom g, const float* __restrict__ idepth_slab,
+                                                                 int* __restrict__ blk_count, const int* __restrict__ items) {
+    const int it = item_of(items, blockIdx.y);
+    const int blk = blockIdx.x;
+    const int l = level_of_block(g, blk);
+    const int i = (blk - g.blk_off[l]) * kCompactBlock + threadIdx.x;
+    const int n = g.rows[l] * g.cols[l];
+    const bool known = (i < n) && !isnan(idepth_slab[size_t(it) * g.pix_total + g.off[l] + i]);
+    const int c = __syncthreads_count(known);
+    if (threadIdx.x == 0) blk_count[size_t(it) * g.blk_total + blk] = c;
+}
+
+// One CTA per (level, stream): exclusive scan of that level's block counts (in place) + total.
+__global__ void __launch_bounds__(1024) k_compact_scan(const Geom g, int* __restrict__ blk_count, int* __restrict__ n_points,
+                                                       const int* __restrict__ items) {
+    __shared__ int warp_sum[32];
+    __shared__ int carry;
+    const int it = item_of(items, blockIdx.y);
+    const int l = blockIdx.x;
+    int* cnt = blk_count + size_t(it) * g.blk_total + g.blk_off[l];
+    const int nb = g.blk_off[l + 1] - g.blk_off[l];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nb; b0 += 1024) {
+        const int i = b0 + threadIdx.x;
+        const int v = i < nb ? cnt[i] : 0;
+        int s = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= d) s += t;
+        }
+        if (lane == 31) warp_sum[w] = s;
+        __syncthreads();
+        if (w == 0) {
+            int ws = warp_sum[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, ws, d);
+                if (lane >= d) ws += t;
+            }
+            warp_sum[lane] = ws;  // inclusive scan of warp totals
+        }
+        __syncthreads();
+        const int before = carry + (w ? warp_sum[w - 1] : 0) + (s - v);
+        if (i < nb) cnt[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) n_points[it * kMaxLevels + l] = carry;
+}
+
+__global__ void __launch_bounds__(kCompactBlock) k_compact_scatter(const Geom g, const float* __restrict__ idepth_slab,
+                                                                   const uint8_t* __restrict__ pyr_slab,
+                                                                   const uint32_t* __restrict__ grad_slab,
+                                                                   const int* __restrict__ blk_base, uint32_t* __restrict__ pk_slab,
+                                                                   float* __restrict__ pt_idepth_slab,
+                                                                   uint32_t* __restrict__ pt_grad_slab,
+                                                                   const int* __restrict__ items) {
+    __shared__ int warp_cnt[32];
+    const int it = item_of(items, blockIdx.y);
+    const size_t base = size_t(it) * g.pix_total;
+    const int blk = blockIdx.x;
+    const int l = level_of_block(g, blk);
+    const int i = (blk - g.blk_off[l]) * kCompactBlock + threadIdx.x;
+    const int R = g.rows[l];
+    const int n = R * g.cols[l];
+    const size_t src = base + g.off[l] + i;
+    float d = 0.0f;
+    bool known = false;
+    if (i < n) {
+        d = idepth_slab[src];
+        known = !isnan(d);
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, known);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) warp_cnt[w] = __popc(ballot);
+    __syncthreads();
+    if (w == 0) {
+        const int v = warp_cnt[lane];
+        int s = v;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, s, k);
+            if (lane >= k) s += t;
+        }
+        warp_cnt[lane] = s - v;  // exclusive
+    }
+    __syncthreads();
+    if (known) {
+        const int pos = blk_base[size_t(it) * g.blk_total + blk] + warp_cnt[w] + __popc(ballot & ((1u << lane) - 1u));
+        const int x = i / R, y = i - x * R;
+        const size_t dst = base + g.off[l] + pos;
+        pk_slab[dst] = uint32_t(x) | (uint32_t(y) << 12) | (uint32_t(pyr_slab[src]) << 24);
+        pt_idepth_slab[dst] = d;
+        pt_grad_slab[dst] = grad_slab[src];
+    }
+}
+
+}  // namespace
+
+namespace {
+__global__ void k_jacobians(const uint32_t* __restrict__ pk, const float* __restrict__ idepth, const uint32_t* __restrict__ grad,
+                            int n, Intrinsics k, float* __restrict__ out6) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t p = pk[i], gr = grad[i];
+    float J[6];
+    jacobian_at(float(int16_t(gr & 0xFFFFu)), float(int16_t(gr >> 16)), float(p & 0xFFFu), float((p >> 12) & 0xFFFu), idepth[i], k,
+                J);
+#pragma unroll
+    for (int a = 0; a < 6; ++a) out6[size_t(i) * 6 + a] = J[a];
+}
+
+__global__ void k_se3_exp(const float* __restrict__ xi6, Pose* __restrict__ out) {
+    float xi[6];
+    for (int a = 0; a < 6; ++a) xi[a] = xi6[a];
+    *out = se3_exp(xi);
+}
+
+inline int grid_for(int n, int block, int cap = 148 * 16) { return max(1, min((n + block - 1) / block, cap)); }
+}  // namespace
+
+// ---- launchers -----------------------------------------------------------------------------------
+void launch_transpose_u8(Launcher& L, const uint8_t* in, uint8_t* out_slab, size_t out_stride, const int* items, int m, int rows,
+                         int cols) {
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, m), block(32, 8);
+    k_transpose<uint8_t><<<grid, block, 0, L.stream>>>(in, out_slab, out_stride, items, rows, cols);
+    ++L.launches;
+}
+void launch_transpose_u16(Launcher& L, const uint16_t* in, uint16_t* out_slab, size_t out_stride, const int* items, int m, int rows,
+                          int cols) {
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, m), block(32, 8);
+    k_transpose<uint16_t><<<grid, block, 0, L.stream>>>(in, out_slab, out_stride, items, rows, cols);
+    ++L.launches;
+}
+void launch_copy_items_u16(Launcher& L, const uint16_t* in, uint16_t* out_slab, size_t out_stride, const int* items, int m,
+                           size_t count) {
+    dim3 grid(grid_for(int(count), 256, 148 * 4), m);
+    k_copy_items_u16<<<grid, 256, 0, L.stream>>>(in, out_slab, out_stride, items, count);
+    ++L.launches;
+}
+void launch_pyramid(Launcher& L, const Geom& g, uint8_t* pyr_slab, const int* items, int m) {
+    for (int l = 1; l < g.L; ++l) {
+        dim3 grid(grid_for(g.rows[l] * g.cols[l], 256), m);
+        k_halve_mean<<<grid, 256, 0, L.stream>>>(g, l, pyr_slab, items);
+        ++L.launches;
+    }
+}
+void launch_gradients(Launcher& L, const Geom& g, const uint8_t* pyr_slab, uint32_t* grad_slab, uint16_t* g2_slab, const int* items,
+                      int m) {
+    dim3 grid(grid_for(g.pix_total, 256), m);
+    k_gradients<<<grid, 256, 0, L.stream>>>(g, pyr_slab, grad_slab, g2_slab, items);
+    ++L.launches;
+}
+void launch_c2f(Launcher& L, const Geom& g, uint16_t thresh, const uint16_t* g2_slab, uint8_t* mask_slab, const int* items, int m) {
+    for (int l = g.L - 2; l >= 0; --l) {
+        const int parents = ((g.rows[l] + 1) / 2) * ((g.cols[l] + 1) / 2);
+        dim3 grid(grid_for(parents, 256), m);
+        k_c2f_level<<<grid, 256, 0, L.stream>>>(g, l, thresh, g2_slab, mask_slab, items);
+        ++L.launches;
+    }
+}
+void launch_idepth(Launcher& L, const Geom& g, const uint16_t* depth_slab, size_t depth_stride, const uint8_t* mask_slab, int dense,
+                   float scale, float variance, float* idepth_slab, float* weight_slab, const int* items, int m) {
+    {
+        dim3 grid(grid_for(g.rows[0] * g.cols[0], 256), m);
+        k_idepth0<<<grid, 256, 0, L.stream>>>(g, depth_slab, depth_stride, mask_slab, dense, scale, variance, idepth_slab,
+                                              weight_slab, items);
+        ++L.launches;
+    }
+    for (int l = 1; l < g.L; ++l) {
+        dim3 grid(grid_for(g.rows[l] * g.cols[l], 256), m);
+        k_idepth_halve<<<grid, 256, 0, L.stream>>>(g, l, idepth_slab, weight_slab, items);
+        ++L.launches;
+    }
+}
+void launch_compact(Launcher& L, const Geom& g, const float* idepth_slab, const uint8_t* pyr_slab, const uint32_t* grad_slab,
+                    int* blk_count, int* n_points, uint32_t* pk_slab, float* pt_idepth_slab, uint32_t* pt_grad_slab,
+                    const int* items, int m) {
+    dim3 gridb(g.blk_total, m);
+    k_compact_count<<<gridb, kCompactBlock, 0, L.stream>>>(g, idepth_slab, blk_count, items);
+    dim3 grids(g.L, m);
+    k_compact_scan<<<grids, 1024, 0, L.stream>>>(g, blk_count, n_points, items);
+    k_compact_scatter<<<gridb, kCompactBlock, 0, L.stream>>>(g, idepth_slab, pyr_slab, grad_slab, blk_count, pk_slab,
+                                                             pt_idepth_slab, pt_grad_slab, items);
+    L.launches += 3;
+}
+void launch_jacobians(Launcher& L, const uint32_t* pk, const float* idepth, const uint32_t* grad, int n, Intrinsics k, float* out6) {
+    if (n <= 0) return;
+    k_jacobians<<<(n + 255) / 256, 256, 0, L.stream>>>(pk, idepth, grad, n, k, out6);
+    ++L.launches;
+}
+void launch_se3_exp(Launcher& L, const float* xi6, Pose* out) {
+    k_se3_exp<<<1, 1, 0, L.stream>>>(xi6, out);
+    ++L.launches;
+}
+
+}  // namespace vors

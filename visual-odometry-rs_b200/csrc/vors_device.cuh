@@ -1,0 +1,144 @@
+// vors_device.cuh — device-side data structures shared by the kernels and the host engine.
+//
+// HBM layout (everything column-major like nalgebra::DMatrix: pixel (row y, col x) at x*rows + y):
+//   * an image pyramid is one slab of `pix_total` elements, level l at pixel offset off[l];
+//   * a keyframe's candidate points are three 4-byte streams per level in the reference's scan order
+//     (extract_z, inverse_compositional.rs:260-279), stored at the same offsets off[l] with capacity
+//     rows_l*cols_l:  pk = x | y<<12 | template<<24,  idepth (f32),  grad = gx(i16) | gy(i16)<<16.
+//     12 B per candidate; the align kernel recomputes the Jacobian and J J^T in registers.
+//   * n streams (trackers) of a batch own consecutive slabs: base + stream * pix_total.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vors_b200.h"
+#include "lie.cuh"
+
+namespace vors {
+
+constexpr int kMaxLevels = VORS_MAX_LEVELS;
+constexpr int kCompactBlock = 1024;  // elements per ordered-compaction block
+constexpr int kTraceCap = 256;       // trace records kept per alignment
+constexpr int kMaxTeam = 160;        // CTAs cooperating on one alignment (<= one per SM)
+constexpr int kNumAcc = 29;          // sum r^2, n_inside, g[6], H[21] (upper triangle)
+
+struct Geom {
+    int L;
+    int rows[kMaxLevels], cols[kMaxLevels];
+    int off[kMaxLevels];         // pixel offset of level l inside a slab
+    int blk_off[kMaxLevels + 1]; // compaction-block offset of level l (kCompactBlock px per block)
+    int pix_total;
+    int blk_total;
+};
+
+// One pyramid level of one alignment, as the align kernel sees it.
+struct LevelJob {
+    const uint32_t* pk;
+    const float* idepth;
+    const uint32_t* grad;
+    const uint8_t* img;  // current frame, this level
+    const int* n_ptr;    // number of candidates (device memory: written by the compaction kernels)
+    int rows, cols;
+    Intrinsics k;
+};
+
+struct AlignJob {
+    LevelJob lv[kMaxLevels];
+    int lvl_first;    // coarsest level to run (nb_levels-1 for a full alignment)
+    int lvl_last;     // finest level to run (0)
+    int flow_level;   // level whose candidates feed the optical-flow test (nb_levels-1); <0 = skip
+    int pass_only;    // 1: single evaluation at `init` on lvl_first, no LM loop (vors_align_pass)
+};
+
+struct AlignResult {
+    Pose model;  // lm_model after the last successful level
+    int status;  // VORS_OK / VORS_OPTIMIZATION_FAILED
+    float optical_flow;
+    int n_iters[kMaxLevels];
+    float energy[kMaxLevels];
+    int n_points[kMaxLevels];
+    int n_passes;
+    int trace_len;
+    unsigned long long point_passes;
+    // pass_only outputs
+    float pass_energy;
+    int pass_n_inside;
+    float pass_g[6];
+    float pass_H[21];
+};
+
+struct TeamScratch {
+    double part[2][kMaxTeam][32];
+    unsigned int counter;
+    unsigned int pad[31];
+};
+
+struct AlignParams {
+    const AlignJob* jobs;
+    const Pose* init;  // per job lm_model prior: current_frame_pose^-1 * keyframe_pose (inverse_compositional.rs:177)
+    AlignResult* results;
+    vors_trace_rec* trace;  // n_jobs * kTraceCap, or nullptr
+    TeamScratch* scratch;   // one per team (only touched when team > 1)
+    int n_jobs;
+    int team;
+    // LM constants (lm_optimizer.rs:115,157,173,179,186)
+    float lm_coef_init, lm_coef_reject_mult, lm_coef_accept_mult, energy_delta_stop;
+    int max_iters, fixed_iters;
+};
+
+// Row J: warp_jacobian_at (inverse_compositional.rs:313-341), used by the align kernel (J is recomputed
+// per pass in registers instead of being stored) and by the jacobian export kernel.  Same expression
+// order as the reference except that `c / fu` is evaluated as c * (1/fu) (loop-invariant reciprocal).
+__device__ __forceinline__ void jacobian_at(float gu, float gv, float u, float v, float rho, const Intrinsics& k, float J[6]) {
+    const float a = u - k.cx;
+    const float b = v - k.cy;
+    const float c = a * k.fy - k.s * b;
+    const float _fv = 1.0f / k.fy;
+    const float _fu = 1.0f / k.fx;
+    const float _fuv = 1.0f / (k.fx * k.fy);
+    J[0] = gu * rho * k.fx;
+    J[1] = rho * (gu * k.s + gv * k.fy);
+    J[2] = -rho * (gu * a + gv * b);
+    J[3] = gu * (-a * b * _fv - k.s) + gv * (-b * b * _fv - k.fy);
+    J[4] = gu * (a * c * _fuv + k.fx) + gv * (b * c * _fuv);
+    J[5] = gu * (-k.fx * k.fx * b + k.s * c) * _fuv + gv * (c * _fu);
+}
+
+// ---- launchers implemented in image_kernels.cu -------------------------------------------------
+// `items`: device array of stream indices the kernels operate on (m of them); nullptr = 0..m-1.
+struct Launcher {
+    cudaStream_t stream;
+    unsigned long long launches = 0;
+};
+
+void launch_transpose_u8(Launcher& L, const uint8_t* in_rowmajor, uint8_t* out_slab, size_t out_stride, const int* items,
+                         int m, int rows, int cols);
+void launch_transpose_u16(Launcher& L, const uint16_t* in_rowmajor, uint16_t* out_slab, size_t out_stride, const int* items,
+                          int m, int rows, int cols);
+void launch_copy_items_u16(Launcher& L, const uint16_t* in, uint16_t* out_slab, size_t out_stride, const int* items, int m,
+                           size_t count);
+void launch_pyramid(Launcher& L, const Geom& g, uint8_t* pyr_slab, const int* items, int m);
+void launch_gradients(Launcher& L, const Geom& g, const uint8_t* pyr_slab, uint32_t* grad_slab, uint16_t* g2_slab,
+                      const int* items, int m);
+void launch_c2f(Launcher& L, const Geom& g, uint16_t thresh, const uint16_t* g2_slab, uint8_t* mask_slab, const int* items,
+                int m);
+void launch_idepth(Launcher& L, const Geom& g, const uint16_t* depth_slab, size_t depth_stride, const uint8_t* mask_slab,
+                   int dense, float scale, float variance, float* idepth_slab, float* weight_slab, const int* items, int m);
+void launch_compact(Launcher& L, const Geom& g, const float* idepth_slab, const uint8_t* pyr_slab, const uint32_t* grad_slab,
+                    int* blk_count, int* n_points, uint32_t* pk_slab, float* pt_idepth_slab, uint32_t* pt_grad_slab,
+                    const int* items, int m);
+void launch_jacobians(Launcher& L, const uint32_t* pk, const float* idepth, const uint32_t* grad, int n, Intrinsics k,
+                      float* out6);
+void launch_se3_exp(Launcher& L, const float* xi6, Pose* out);
+
+// ---- implemented in align_kernel.cu ---------------------------------------------------------------
+struct AlignLaunchInfo {
+    int block;
+    int max_resident_ctas;  // co-resident CTAs of the align kernel on this device
+    int sm_count;
+};
+cudaError_t align_query(AlignLaunchInfo* info);
+cudaError_t launch_align(Launcher& L, const AlignParams& p, int n_teams);
+
+}  // namespace vors
