@@ -174,14 +174,12 @@ def scene_config_kwargs(scene: Scene):
 # ------------------------------------------------------------------------------------------
 # torch back-end (bench only): renders a batch of frames on the GPU.
 
-def render_batch_torch(scene: Scene, poses, device, frame_seed: int = 0):
-    """poses: list of (t, q).  Returns (gray u8 [B, rows, cols], depth u16-as-int32 [B, rows, cols]) torch tensors."""
+def render_batch_torch(scene: Scene, poses, device, frame_seed: int = 0, chunk: int = 16):
+    """Same maths as render(), vectorised over frames on `device`.  poses: list of (t, q).
+    Returns (gray u8 [B, rows, cols], depth int32 [B, rows, cols]) torch tensors (depth fits u16)."""
     import torch
 
-    B = len(poses)
     dt = torch.float64
-    t = torch.tensor(np.stack([p[0] for p in poses]), dtype=dt, device=device)  # B,3
-    R = torch.tensor(np.stack([quat_to_rot(p[1]) for p in poses]), dtype=dt, device=device)  # B,3,3
     ys, xs = torch.meshgrid(torch.arange(scene.rows, dtype=dt, device=device),
                             torch.arange(scene.cols, dtype=dt, device=device), indexing="ij")
     rc = torch.stack([(xs - scene.cx) / scene.fx, (ys - scene.cy) / scene.fy, torch.ones_like(xs)], -1)  # r,c,3
@@ -192,18 +190,21 @@ def render_batch_torch(scene: Scene, poses, device, frame_seed: int = 0):
     gen = torch.Generator(device=device)
     gen.manual_seed(int(scene.seed) * 1000003 + frame_seed)
     grays, depths = [], []
-    for b in range(B):
-        rw = rc @ R[b].T
+    for b0 in range(0, len(poses), chunk):
+        sub = poses[b0:b0 + chunk]
+        t = torch.tensor(np.stack([p[0] for p in sub]), dtype=dt, device=device)  # b,3
+        R = torch.tensor(np.stack([quat_to_rot(p[1]) for p in sub]), dtype=dt, device=device)  # b,3,3
+        rw = torch.einsum("rck,bjk->brcj", rc, R)  # world-frame rays
         denom = rw @ n
         denom = torch.where(denom.abs() < 1e-9, torch.full_like(denom, 1e-9), denom)
-        lam = (scene.dist - (n @ t[b])) / denom
-        Xw = t[b] + lam[..., None] * rw
+        lam = (scene.dist - (t @ n))[:, None, None] / denom
+        Xw = t[:, None, None, :] + lam[..., None] * rw
         p, q = Xw @ e1, Xw @ e2
         tex = torch.full_like(p, 128.0)
         for (fx_, fy_), ph, a in zip(scene.freqs, scene.phases, scene.amps):
-            tex = tex + float(a) * torch.sin(2 * np.pi * (float(fx_) * p + float(fy_) * q) + float(ph))
-        tex = tex + torch.randn(tex.shape, generator=gen, device=device, dtype=dt) * scene.noise_sigma
+            tex += float(a) * torch.sin(2 * np.pi * (float(fx_) * p + float(fy_) * q) + float(ph))
+        tex += torch.randn(tex.shape, generator=gen, device=device, dtype=dt) * scene.noise_sigma
         grays.append(torch.clamp(torch.round(tex), 0, 255).to(torch.uint8))
         valid = (lam > 0.1) & (lam < 13.0)
         depths.append(torch.where(valid, torch.round(lam * DEPTH_SCALE), torch.zeros_like(lam)).to(torch.int32))
-    return torch.stack(grays), torch.stack(depths)
+    return torch.cat(grays), torch.cat(depths)
