@@ -4,8 +4,11 @@
 // walks the pyramid coarse to fine and, per level, runs the reference's Levenberg-Marquardt loop
 // (src/math/optimizer.rs:57-70 + src/core/track/lm_optimizer.rs:113-192) entirely on the device:
 //
-//   pass      every thread streams its share of the level's candidates (12 B each, coalesced), warps
-//             them with the folded 3x4 matrix of lie.cuh (lm_optimizer.rs:213-219), tests the
+//   pass      the level's candidate streams (12 B per candidate) are staged by TMA bulk copies
+//             (cp.async.bulk + mbarrier, a private ring of kStages x 64 candidates per warp, refilled by
+//             lane 0 as soon as the warp has read a stage), so HBM latency is covered by ~74 KB in flight
+//             per SM instead of by occupancy; each lane evaluates two candidates per stage, branch-free:
+//             warps them with the folded 3x4 matrix of lie.cuh (lm_optimizer.rs:213-219), tests the
 //             reference's conservative inside rule and samples the current image bilinearly from u8
 //             texels in f32 (lm_optimizer.rs:227-251), forms the residual against the template
 //             value, recomputes the Jacobian (inverse_compositional.rs:313-341) and accumulates
@@ -31,6 +34,9 @@ namespace {
 
 constexpr int kBlock = 256;
 constexpr int kWarps = kBlock / 32;
+constexpr int kStages = 6;                    // TMA ring depth per warp
+constexpr int kStageWords = 3 * kChunk;       // pk | idepth | grad, kChunk 4-byte words each
+constexpr uint32_t kChunkBytes = kChunk * 4;  // bytes per stream per stage
 
 struct LmShared {
     float M[12];
@@ -51,7 +57,38 @@ struct LmShared {
     unsigned long long point_passes;
     float warp_part[kWarps][32];
     double tot[32];
+    alignas(8) unsigned long long full_bar[kWarps][kStages];
+    alignas(128) float ring[kWarps][kStages * kStageWords];
 };
+
+// ---- TMA bulk copy + mbarrier primitives (PTX ISA: cp.async.bulk, mbarrier) ------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// int -> float without the XU pipe: 0x4B000000 | v is the float 2^23 + v for v < 2^23.
+__device__ __forceinline__ float u2f(uint32_t v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }
+__device__ __forceinline__ float s16_2f(uint32_t v16) { return __uint_as_float(0x4B000000u | (v16 ^ 0x8000u)) - 8421376.0f; }
+
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
@@ -98,11 +135,14 @@ __device__ __noinline__ void warp_exact(const Pose& m, const Intrinsics& k, floa
 
 constexpr float kBandPx = 1.0f / 128.0f;
 
-// One candidate: warp, inside test, bilinear sample, residual, Jacobian, accumulate.
-__device__ __forceinline__ void eval_point(uint32_t pk, float rho, uint32_t gr, const float (&M)[12], const Intrinsics& k,
-                                           const Pose* __restrict__ model, const uint8_t* __restrict__ img, int rows, float wm2,
-                                           float hm2, Acc& acc) {
-    const float x = float(pk & 0xFFFu), y = float((pk >> 12) & 0xFFFu);
+// One candidate, branch-free (so the four texel gathers issue early and the Jacobian arithmetic overlaps their
+// latency): warp, inside test, bilinear sample, residual, Jacobian, accumulate.  `live` is false for the padding
+// lanes of a partial last chunk.  Outside / padding candidates read texel (0,0) and contribute exact zeros.
+__device__ __forceinline__ void eval_point(bool live, uint32_t pk, float rho, uint32_t gr, const float (&M)[12], const Intrinsics& k,
+                                           const Pose* __restrict__ model, const uint8_t* __restrict__ img, int rows, int wm2i,
+                                           int hm2i, float wm2, float hm2, Acc& acc) {
+    rho = live ? rho : 1.0f;  // padding lanes must stay finite (0 * NaN would poison the sums)
+    const float x = u2f(pk & 0xFFFu), y = u2f((pk >> 12) & 0xFFFu);
     const float U = fmaf(M[0], x, fmaf(M[1], y, fmaf(M[3], rho, M[2])));
     const float V = fmaf(M[4], x, fmaf(M[5], y, fmaf(M[7], rho, M[6])));
     const float W = fmaf(M[8], x, fmaf(M[9], y, fmaf(M[11], rho, M[10])));
@@ -110,26 +150,27 @@ __device__ __forceinline__ void eval_point(uint32_t pk, float rho, uint32_t gr, 
     float u = U * iw, v = V * iw;
     if (fabsf(u) < kBandPx || fabsf(u - wm2) < kBandPx || fabsf(v) < kBandPx || fabsf(v - hm2) < kBandPx)
         warp_exact(*model, k, x, y, rho, u, v);
-    const float u0 = floorf(u), v0 = floorf(v);
-    // lm_optimizer.rs:231: inside iff 0 <= floor(u) < W-2 and 0 <= floor(v) < H-2 (NaN fails)
-    if (u0 >= 0.0f && u0 < wm2 && v0 >= 0.0f && v0 < hm2) {
-        const uint8_t* p = img + size_t(int(u0)) * rows + int(v0);
-        const float i00 = float(__ldg(p)), i10 = float(__ldg(p + 1));
-        const float i01 = float(__ldg(p + rows)), i11 = float(__ldg(p + rows + 1));
-        const float a = u - u0, b = v - v0;
-        const float val = (1.0f - b) * (1.0f - a) * i00 + b * (1.0f - a) * i10 + (1.0f - b) * a * i01 + b * a * i11;
-        const float r = val - float(pk >> 24);
-        float J[6];
-        jacobian_at(float(int16_t(gr & 0xFFFFu)), float(int16_t(gr >> 16)), x, y, rho, k, J);
-        acc.e = fmaf(r, r, acc.e);
-        acc.n += 1.0f;
+    // lm_optimizer.rs:231: inside iff 0 <= floor(u) < W-2 and 0 <= floor(v) < H-2; NaN coordinates are outside
+    // (float->int of NaN is 0, so NaN needs its own test; +-inf saturate and fail the range test).
+    const int iu = __float2int_rd(u), iv = __float2int_rd(v);
+    const bool inside = live && (unsigned(iu) < unsigned(wm2i)) && (unsigned(iv) < unsigned(hm2i)) && ((u + v) == (u + v));
+    const uint8_t* p = img + (inside ? iu * rows + iv : 0);
+    const uint32_t t00 = __ldg(p), t10 = __ldg(p + 1), t01 = __ldg(p + rows), t11 = __ldg(p + rows + 1);
+    // Jacobian (independent of the texels): zero gradient for outside candidates zeroes J, g and H contributions
+    const float gu = inside ? s16_2f(gr & 0xFFFFu) : 0.0f, gv = inside ? s16_2f(gr >> 16) : 0.0f;
+    float J[6];
+    jacobian_at(gu, gv, x, y, rho, k, J);
+    const float a = u - u2f(uint32_t(iu) & 0xFFFu), b = v - u2f(uint32_t(iv) & 0xFFFu);
+    const float val = (1.0f - b) * (1.0f - a) * u2f(t00) + b * (1.0f - a) * u2f(t10) + (1.0f - b) * a * u2f(t01) + b * a * u2f(t11);
+    const float r = inside ? val - u2f(pk >> 24) : 0.0f;
+    acc.e = fmaf(r, r, acc.e);
+    acc.n += inside ? 1.0f : 0.0f;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) acc.g[c] = fmaf(J[c], r, acc.g[c]);
+    for (int c = 0; c < 6; ++c) acc.g[c] = fmaf(J[c], r, acc.g[c]);
 #pragma unroll
-        for (int c = 0; c < 6; ++c)
+    for (int c = 0; c < 6; ++c)
 #pragma unroll
-            for (int d = c; d < 6; ++d) acc.h[tri(c, d)] = fmaf(J[c], J[d], acc.h[tri(c, d)]);
-    }
+        for (int d = c; d < 6; ++d) acc.h[tri(c, d)] = fmaf(J[c], J[d], acc.h[tri(c, d)]);
 }
 
 // The serial part of one LM round, run by thread 0 of every CTA of the team on identical inputs.
@@ -209,6 +250,13 @@ __global__ void __launch_bounds__(kBlock, 2) k_align(const AlignParams P) {
     const int n_teams = gridDim.x / team;
     TeamScratch* scratch = team > 1 ? P.scratch + team_id : nullptr;
     unsigned epoch = 0;  // passes this team has synchronised on so far (same in every CTA of the team)
+    uint32_t phase_bits = 0;  // per-warp: parity to wait for next on each ring stage
+    if (tid == 0) {
+        for (int w = 0; w < kWarps; ++w)
+            for (int st = 0; st < kStages; ++st) mbar_init(smem_u32(&S.full_bar[w][st]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
     for (int job_idx = team_id; job_idx < P.n_jobs; job_idx += n_teams) {
         const AlignJob& job = P.jobs[job_idx];
@@ -226,7 +274,8 @@ __global__ void __launch_bounds__(kBlock, 2) k_align(const AlignParams P) {
             const LevelJob& lj = job.lv[lvl];
             const int n = *lj.n_ptr;
             const int rows = lj.rows;
-            const float wm2 = float(lj.cols - 2), hm2 = float(rows - 2);
+            const int wm2i = lj.cols - 2, hm2i = rows - 2;
+            const float wm2 = float(wm2i), hm2 = float(hm2i);
             const Intrinsics k = lj.k;
             const uint32_t* __restrict__ pk = lj.pk;
             const float* __restrict__ idp = lj.idepth;
@@ -251,10 +300,45 @@ __global__ void __launch_bounds__(kBlock, 2) k_align(const AlignParams P) {
 #pragma unroll
                 for (int c = 0; c < 21; ++c) acc.h[c] = 0.0f;
 
-                // ---- pass: candidates interleaved over the team's threads (coalesced 4-byte streams)
-                const int stride = team * kBlock;
-#pragma unroll 2
-                for (int i = rank * kBlock + tid; i < n; i += stride) eval_point(pk[i], idp[i], grd[i], M, k, &S.cand_model, img, rows, wm2, hm2, acc);
+                // ---- pass: this warp owns chunks gw, gw + TW, ... of kChunk candidates; its ring of kStages
+                // stages is filled by TMA bulk copies (3 x 256 B per stage) that complete on the stage's mbarrier.
+                {
+                    const int n_chunks = (n + kChunk - 1) / kChunk;
+                    const int TW = team * kWarps, gw = rank * kWarps + warp;
+                    float* ring = S.ring[warp];
+                    auto fill = [&](int stage, int chunk) {  // lane 0 only
+                        const uint32_t bar = smem_u32(&S.full_bar[warp][stage]);
+                        const uint32_t dst = smem_u32(ring + stage * kStageWords);
+                        const size_t e0 = size_t(chunk) * kChunk;
+                        mbar_expect_tx(bar, 3 * kChunkBytes);
+                        bulk_g2s(dst, pk + e0, kChunkBytes, bar);
+                        bulk_g2s(dst + kChunkBytes, idp + e0, kChunkBytes, bar);
+                        bulk_g2s(dst + 2 * kChunkBytes, grd + e0, kChunkBytes, bar);
+                    };
+                    if (lane == 0) {
+#pragma unroll
+                        for (int st = 0; st < kStages; ++st)
+                            if (gw + st * TW < n_chunks) fill(st, gw + st * TW);
+                    }
+                    int stage = 0;
+                    for (int c = gw; c < n_chunks; c += TW) {
+                        mbar_wait(smem_u32(&S.full_bar[warp][stage]), (phase_bits >> stage) & 1u);
+                        phase_bits ^= 1u << stage;
+                        const float* sp = ring + stage * kStageWords;
+                        const uint32_t pk0 = __float_as_uint(sp[lane]), pk1 = __float_as_uint(sp[lane + 32]);
+                        const float rho0 = sp[kChunk + lane], rho1 = sp[kChunk + lane + 32];
+                        const uint32_t gr0 = __float_as_uint(sp[2 * kChunk + lane]), gr1 = __float_as_uint(sp[2 * kChunk + lane + 32]);
+                        __syncwarp();
+                        if (lane == 0 && c + kStages * TW < n_chunks) {
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // order our reads before the refill
+                            fill(stage, c + kStages * TW);
+                        }
+                        const int i0 = c * kChunk + lane;
+                        eval_point(i0 < n, pk0, rho0, gr0, M, k, &S.cand_model, img, rows, wm2i, hm2i, wm2, hm2, acc);
+                        eval_point(i0 + 32 < n, pk1, rho1, gr1, M, k, &S.cand_model, img, rows, wm2i, hm2i, wm2, hm2, acc);
+                        stage = (stage + 1 == kStages) ? 0 : stage + 1;
+                    }
+                }
 
                 // ---- reduce: warp shuffle, then per-CTA f64 sums in fixed order
                 float vals[kNumAcc];

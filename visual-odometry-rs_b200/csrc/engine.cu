@@ -170,13 +170,15 @@ class Engine {
         if (prop.major != 10) return fail(VORS_E_CUDA, "libvors_b200 is built for sm_100a only; device is not compute capability 10.x");
 
         g.L = levels;
-        int off = 0, boff = 0;
+        int off = 0, boff = 0, poff = 0;
         Intrinsics k{cfg.fx, cfg.fy, cfg.cx, cfg.cy, cfg.skew};
         for (int l = 0; l < levels; ++l) {
             g.rows[l] = int(lr[l]);
             g.cols[l] = int(lc[l]);
             g.off[l] = off;
             g.blk_off[l] = boff;
+            g.pt_off[l] = poff;
+            poff += (g.rows[l] * g.cols[l] + kChunk - 1) / kChunk * kChunk;
             off += g.rows[l] * g.cols[l];
             boff += (g.rows[l] * g.cols[l] + kCompactBlock - 1) / kCompactBlock;
             intr[l] = k;  // camera.rs:106-108 `multi_res`
@@ -184,6 +186,7 @@ class Engine {
         }
         for (int l = levels; l <= kMaxLevels; ++l) g.blk_off[l] = boff;
         g.pix_total = off;
+        g.pt_total = poff;
         g.blk_total = boff;
 
         CU_TRY(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
@@ -191,7 +194,7 @@ class Engine {
         CU_TRY(align_query(&info));
         if (info.max_resident_ctas < 1) return fail(VORS_E_CUDA, "align kernel cannot be resident on this device");
 
-        const size_t N = size_t(n), P = size_t(g.pix_total), I = size_t(rows) * cols;
+        const size_t N = size_t(n), P = size_t(g.pix_total), I = size_t(rows) * cols, PT = size_t(g.pt_total);
         CU_TRY(cudaMalloc(&d_pyr, N * P));
         CU_TRY(cudaMalloc(&d_stage8, N * I));
         CU_TRY(cudaMalloc(&d_stage16, N * I * 2));
@@ -201,9 +204,13 @@ class Engine {
         CU_TRY(cudaMalloc(&d_mask, N * P));
         CU_TRY(cudaMalloc(&d_idepth, N * P * 4));
         CU_TRY(cudaMalloc(&d_weight, N * P * 4));
-        CU_TRY(cudaMalloc(&d_pk, N * P * 4));
-        CU_TRY(cudaMalloc(&d_pt_idepth, N * P * 4));
-        CU_TRY(cudaMalloc(&d_pt_grad, N * P * 4));
+        CU_TRY(cudaMalloc(&d_pk, N * PT * 4));
+        CU_TRY(cudaMalloc(&d_pt_idepth, N * PT * 4));
+        CU_TRY(cudaMalloc(&d_pt_grad, N * PT * 4));
+        // bulk copies of a partial last chunk read up to 15 B past the last candidate: keep it initialised
+        CU_TRY(cudaMemsetAsync(d_pk, 0, N * PT * 4, L.stream));
+        CU_TRY(cudaMemsetAsync(d_pt_idepth, 0, N * PT * 4, L.stream));
+        CU_TRY(cudaMemsetAsync(d_pt_grad, 0, N * PT * 4, L.stream));
         CU_TRY(cudaMalloc(&d_blk_count, N * size_t(g.blk_total) * 4));
         CU_TRY(cudaMalloc(&d_n_points, N * kMaxLevels * 4));
         CU_TRY(cudaMalloc(&d_items, N * 4));
@@ -232,11 +239,12 @@ class Engine {
     void fill_job(AlignJob& j, int stream, int lvl_first, int lvl_last, int flow_level, int pass_only) const {
         std::memset(&j, 0, sizeof(j));
         const size_t base = size_t(stream) * g.pix_total;
+        const size_t pbase = size_t(stream) * g.pt_total;
         for (int l = 0; l < g.L; ++l) {
             LevelJob& lj = j.lv[l];
-            lj.pk = d_pk + base + g.off[l];
-            lj.idepth = d_pt_idepth + base + g.off[l];
-            lj.grad = d_pt_grad + base + g.off[l];
+            lj.pk = d_pk + pbase + g.pt_off[l];
+            lj.idepth = d_pt_idepth + pbase + g.pt_off[l];
+            lj.grad = d_pt_grad + pbase + g.pt_off[l];
             lj.img = d_pyr + base + g.off[l];
             lj.n_ptr = d_n_points + stream * kMaxLevels + l;
             lj.rows = g.rows[l];
@@ -838,7 +846,7 @@ int vors_keyframe_points(const vors_keyframe* kf, uint32_t level, uint32_t* xy, 
     const int np = e->h_n_points[level];
     if (np == 0) return VORS_OK;
     CU_TRY(cudaSetDevice(e->device));
-    const size_t off = size_t(e->g.off[level]);
+    const size_t off = size_t(e->g.pt_off[level]);
     const size_t cnt = size_t(np);
     std::vector<uint32_t> pk(cnt), gr(cnt);
     CU_TRY(cudaMemcpy(pk.data(), e->d_pk + off, size_t(np) * 4, cudaMemcpyDeviceToHost));
@@ -866,7 +874,7 @@ int vors_keyframe_jacobians(const vors_keyframe* kf, uint32_t level, float* jac6
     CU_TRY(cudaSetDevice(e->device));
     int rc = e->need_tmp(size_t(np) * 24);
     if (rc != VORS_OK) return rc;
-    const size_t off = size_t(e->g.off[level]);
+    const size_t off = size_t(e->g.pt_off[level]);
     launch_jacobians(e->L, e->d_pk + off, e->d_pt_idepth + off, e->d_pt_grad + off, np, e->intr[level], e->d_tmp);
     CU_TRY(cudaMemcpyAsync(jac6, e->d_tmp, size_t(np) * 24, cudaMemcpyDeviceToHost, e->L.stream));
     CU_TRY(cudaStreamSynchronize(e->L.stream));

@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(kCompactBlock) k_compact_scatter(const Geom g,
     if (known) {
         const int pos = blk_base[size_t(it) * g.blk_total + blk] + warp_cnt[w] + __popc(ballot & ((1u << lane) - 1u));
         const int x = i / R, y = i - x * R;
-        const size_t dst = base + g.off[l] + pos;
+        const size_t dst = size_t(it) * g.pt_total + g.pt_off[l] + pos;
         pk_slab[dst] = uint32_t(x) | (uint32_t(y) << 12) | (uint32_t(pyr_slab[src]) << 24);
         pt_idepth_slab[dst] = d;
         pt_grad_slab[dst] = grad_slab[src];

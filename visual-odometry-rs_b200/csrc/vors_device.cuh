@@ -3,10 +3,10 @@
 // HBM layout (everything column-major like nalgebra::DMatrix: pixel (row y, col x) at x*rows + y):
 //   * an image pyramid is one slab of `pix_total` elements, level l at pixel offset off[l];
 //   * a keyframe's candidate points are three 4-byte streams per level in the reference's scan order
-//     (extract_z, inverse_compositional.rs:260-279), stored at the same offsets off[l] with capacity
-//     rows_l*cols_l:  pk = x | y<<12 | template<<24,  idepth (f32),  grad = gx(i16) | gy(i16)<<16.
+//     (extract_z, inverse_compositional.rs:260-279), stored at 256-byte aligned offsets pt_off[l] with capacity
+//     rows_l*cols_l (so the align kernel can stage them with 16-byte aligned bulk copies):  pk = x | y<<12 | template<<24,  idepth (f32),  grad = gx(i16) | gy(i16)<<16.
 //     12 B per candidate; the align kernel recomputes the Jacobian and J J^T in registers.
-//   * n streams (trackers) of a batch own consecutive slabs: base + stream * pix_total.
+//   * n streams (trackers) of a batch own consecutive slabs: base + stream * pix_total (pt_total for candidates).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -21,12 +21,15 @@ constexpr int kMaxLevels = VORS_MAX_LEVELS;
 constexpr int kCompactBlock = 1024;  // elements per ordered-compaction block
 constexpr int kTraceCap = 256;       // trace records kept per alignment
 constexpr int kMaxTeam = 160;        // CTAs cooperating on one alignment (<= one per SM)
+constexpr int kChunk = 64;          // candidates per warp-stage of the align kernel's TMA ring (256 B per stream)
 constexpr int kNumAcc = 29;          // sum r^2, n_inside, g[6], H[21] (upper triangle)
 
 struct Geom {
     int L;
     int rows[kMaxLevels], cols[kMaxLevels];
     int off[kMaxLevels];         // pixel offset of level l inside a slab
+    int pt_off[kMaxLevels];      // element offset of level l inside a candidate-stream slab (kChunk-aligned for TMA)
+    int pt_total;                // candidate-stream slab extent per stream (kChunk-aligned)
     int blk_off[kMaxLevels + 1]; // compaction-block offset of level l (kCompactBlock px per block)
     int pix_total;
     int blk_total;
