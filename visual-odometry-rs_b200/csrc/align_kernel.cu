@@ -4,16 +4,17 @@
 // walks the pyramid coarse to fine and, per level, runs the reference's Levenberg-Marquardt loop
 // (src/math/optimizer.rs:57-70 + src/core/track/lm_optimizer.rs:113-192) entirely on the device:
 //
-//   pass      the level's candidate streams (12 B per candidate) are staged by TMA bulk copies
-//             (cp.async.bulk + mbarrier, a private ring of kStages x 64 candidates per warp, refilled by
-//             lane 0 as soon as the warp has read a stage), so HBM latency is covered by ~74 KB in flight
-//             per SM instead of by occupancy; each lane evaluates two candidates per stage, branch-free:
-//             warps them with the folded 3x4 matrix of lie.cuh (lm_optimizer.rs:213-219), tests the
-//             reference's conservative inside rule and samples the current image bilinearly from u8
-//             texels in f32 (lm_optimizer.rs:227-251), forms the residual against the template
-//             value, recomputes the Jacobian (inverse_compositional.rs:313-341) and accumulates
-//             sum r^2, n_inside, g = sum J r and the 21 unique entries of H = sum J J^T in registers
-//             (eval_energy + compute_eval_data, lm_optimizer.rs:68-107, fused and speculative);
+//   pass      warp-specialised.  A PRODUCER warp stages the level's three candidate streams (12 B per
+//             candidate) into shared memory with TMA bulk copies (cp.async.bulk, SASS UBLKCP) through a
+//             full/empty mbarrier ring of kStages x 64 candidates per consumer warp, so HBM latency is
+//             covered by ~74 KB in flight per SM instead of by occupancy.  Eight CONSUMER warps evaluate
+//             two candidates per lane per stage, branch-free: warp with the folded 3x4 matrix of lie.cuh
+//             (lm_optimizer.rs:213-219), the reference's conservative inside rule, f32 bilinear sample of
+//             u8 texels (lm_optimizer.rs:227-251), residual against the template value, Jacobian recomputed
+//             in registers (inverse_compositional.rs:313-341), and sum r^2, n_inside, g = sum J r.
+//             H = sum J J^T over the inside set is formed as H_total - H_outside: H_total is precomputed per
+//             keyframe level (k_h_total), so only candidates that fall outside accumulate J J^T, under a
+//             warp-uniform branch (eval_energy + compute_eval_data, lm_optimizer.rs:68-107, fused);
 //   reduce    warp shuffles -> shared memory -> f64 per-CTA partials -> (team > 1) peer partials
 //             through global memory with one counter barrier per pass; fixed order => deterministic;
 //   decide    thread 0 of every CTA redundantly replays accept / reject / stop (lm_optimizer.rs:
@@ -23,7 +24,8 @@
 //
 // team == 1 is the throughput configuration (one alignment per CTA, two CTAs per SM so one CTA's
 // serial solve overlaps the other's pass); team > 1 trades efficiency for latency on few streams.
-// No tensor cores: 29 accumulators per candidate, bounded by the fp32 pipe and memory latency.
+// No tensor cores: the work is ~130 scalar f32 instructions per 12-byte candidate, bounded by
+// instruction issue, not by a dense contraction.
 #include <cooperative_groups.h>
 
 #include "vors_device.cuh"
@@ -32,11 +34,12 @@ namespace vors {
 
 namespace {
 
-constexpr int kBlock = 256;
-constexpr int kWarps = kBlock / 32;
-constexpr int kStages = 6;                    // TMA ring depth per warp
-constexpr int kStageWords = 3 * kChunk;       // pk | idepth | grad, kChunk 4-byte words each
-constexpr uint32_t kChunkBytes = kChunk * 4;  // bytes per stream per stage
+constexpr int kWarps = 7;                     // consumer warps per CTA (7 + 1 producer = 8 warps: 2 CTAs/SM at up to 128 registers)
+constexpr int kConsumers = kWarps * 32;
+constexpr int kBlock = kConsumers + 32;       // + one producer warp
+constexpr int kStages = 6;                    // TMA ring depth per consumer warp
+constexpr int kStageWords = 3 * kChunk;       // pk | idepth | grad, kChunk 4-byte words each (one chunk-blocked record)
+constexpr uint32_t kStageBytes = kStageWords * 4;
 
 struct LmShared {
     float M[12];
@@ -58,6 +61,7 @@ struct LmShared {
     float warp_part[kWarps][32];
     double tot[32];
     alignas(8) unsigned long long full_bar[kWarps][kStages];
+    alignas(8) unsigned long long empty_bar[kWarps][kStages];
     alignas(128) float ring[kWarps][kStages * kStageWords];
 };
 
@@ -69,10 +73,27 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// candidates are streamed once per pass: evict-first in L2 so the frame images (re-read by every pass) stay resident
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(policy)
                  : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // non-blocking
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    return done != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
@@ -88,7 +109,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // int -> float without the XU pipe: 0x4B000000 | v is the float 2^23 + v for v < 2^23.
 __device__ __forceinline__ float u2f(uint32_t v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }
 __device__ __forceinline__ float s16_2f(uint32_t v16) { return __uint_as_float(0x4B000000u | (v16 ^ 0x8000u)) - 8421376.0f; }
-
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
@@ -102,7 +127,7 @@ __device__ __host__ constexpr int tri(int a, int b) { return a * 6 - a * (a - 1)
 struct Acc {
     float e, n;
     float g[6];
-    float h[21];
+    float h[21];  // J J^T of the candidates that fell OUTSIDE (subtracted from H_total)
 };
 
 // The reference's own warp arithmetic (lm_optimizer.rs:213-219 with camera.rs:126-140 and nalgebra's
@@ -110,7 +135,7 @@ struct Acc {
 // separately like rustc emits it.  Only used for candidates that land within kBandPx of an inside-test
 // boundary, where the sign of the last ulp decides membership (e.g. the x = 0 column under an identity
 // model): there the folded matrix and the reference may disagree, so the reference's order decides.
-__device__ __noinline__ void warp_exact(const Pose& m, const Intrinsics& k, float x, float y, float rho, float& u, float& v) {
+__device__ __noinline__ float2 warp_exact(const Pose& m, const Intrinsics& k, float x, float y, float rho) {
     const float z = __fdiv_rn(1.0f, rho);
     const float Y = __fdiv_rn(__fmul_rn(__fsub_rn(y, k.cy), z), k.fy);
     const float X = __fdiv_rn(__fsub_rn(__fmul_rn(__fsub_rn(x, k.cx), z), __fmul_rn(k.s, Y)), k.fx);
@@ -129,48 +154,80 @@ __device__ __noinline__ void warp_exact(const Pose& m, const Intrinsics& k, floa
     const float Z2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(tz, qw), cz), z), m.t.z);
     const float px = __fadd_rn(__fadd_rn(__fmul_rn(k.fx, X2), __fmul_rn(k.s, Y2)), __fmul_rn(k.cx, Z2));
     const float py = __fadd_rn(__fmul_rn(k.fy, Y2), __fmul_rn(k.cy, Z2));
-    u = __fdiv_rn(px, Z2);
-    v = __fdiv_rn(py, Z2);
+    return make_float2(__fdiv_rn(px, Z2), __fdiv_rn(py, Z2));
 }
 
 constexpr float kBandPx = 1.0f / 128.0f;
 
-// One candidate, branch-free (so the four texel gathers issue early and the Jacobian arithmetic overlaps their
-// latency): warp, inside test, bilinear sample, residual, Jacobian, accumulate.  `live` is false for the padding
-// lanes of a partial last chunk.  Outside / padding candidates read texel (0,0) and contribute exact zeros.
-__device__ __forceinline__ void eval_point(bool live, uint32_t pk, float rho, uint32_t gr, const float (&M)[12], const Intrinsics& k,
-                                           const Pose* __restrict__ model, const uint8_t* __restrict__ img, int rows, int wm2i,
-                                           int hm2i, float wm2, float hm2, Acc& acc) {
+// A candidate between its gather issue (front) and its arithmetic (back).  The consumer loop runs the front of
+// candidate q+1 before the back of candidate q, so texel latency (L1 miss -> L2) hides behind ~170 instructions.
+struct Front {
+    uint32_t pk, gr;
+    float rho, a, b;
+    uint32_t t00, t10, t01, t11;
+    bool live, inside;
+};
+
+// front: warp, inside test, texel gathers (branch-free on the common path; `live` is false for the padding lanes
+// of a partial last chunk; outside / padding candidates read texel (0,0) and later contribute exact zeros).
+__device__ __forceinline__ void front(bool live, uint32_t pk, float rho, uint32_t gr, const float (&M)[12], const Intrinsics& k,
+                                      const Pose* __restrict__ model, const uint8_t* __restrict__ img, int rows, int wm2i, int hm2i,
+                                      float wm2, float hm2, Front& f) {
     rho = live ? rho : 1.0f;  // padding lanes must stay finite (0 * NaN would poison the sums)
     const float x = u2f(pk & 0xFFFu), y = u2f((pk >> 12) & 0xFFFu);
     const float U = fmaf(M[0], x, fmaf(M[1], y, fmaf(M[3], rho, M[2])));
     const float V = fmaf(M[4], x, fmaf(M[5], y, fmaf(M[7], rho, M[6])));
     const float W = fmaf(M[8], x, fmaf(M[9], y, fmaf(M[11], rho, M[10])));
-    const float iw = __frcp_rn(W);
+    const float iw = rcp_approx(W);
     float u = U * iw, v = V * iw;
-    if (fabsf(u) < kBandPx || fabsf(u - wm2) < kBandPx || fabsf(v) < kBandPx || fabsf(v - hm2) < kBandPx)
-        warp_exact(*model, k, x, y, rho, u, v);
+    // within kBandPx of an inside-test boundary the reference's own arithmetic decides (rare)
+    const float band = fminf(fminf(fabsf(u), fabsf(u - wm2)), fminf(fabsf(v), fabsf(v - hm2)));
+    if (band < kBandPx) {
+        const float2 uv = warp_exact(*model, k, x, y, rho);
+        u = uv.x;
+        v = uv.y;
+    }
     // lm_optimizer.rs:231: inside iff 0 <= floor(u) < W-2 and 0 <= floor(v) < H-2; NaN coordinates are outside
     // (float->int of NaN is 0, so NaN needs its own test; +-inf saturate and fail the range test).
     const int iu = __float2int_rd(u), iv = __float2int_rd(v);
     const bool inside = live && (unsigned(iu) < unsigned(wm2i)) && (unsigned(iv) < unsigned(hm2i)) && ((u + v) == (u + v));
     const uint8_t* p = img + (inside ? iu * rows + iv : 0);
-    const uint32_t t00 = __ldg(p), t10 = __ldg(p + 1), t01 = __ldg(p + rows), t11 = __ldg(p + rows + 1);
-    // Jacobian (independent of the texels): zero gradient for outside candidates zeroes J, g and H contributions
-    const float gu = inside ? s16_2f(gr & 0xFFFFu) : 0.0f, gv = inside ? s16_2f(gr >> 16) : 0.0f;
+    f.t00 = __ldg(p);
+    f.t10 = __ldg(p + 1);
+    f.t01 = __ldg(p + rows);
+    f.t11 = __ldg(p + rows + 1);
+    f.a = u - u2f(uint32_t(iu) & 0xFFFu);
+    f.b = v - u2f(uint32_t(iv) & 0xFFFu);
+    f.pk = pk;
+    f.gr = gr;
+    f.rho = rho;
+    f.live = live;
+    f.inside = inside;
+}
+
+// back: Jacobian, bilinear sample, residual, accumulate.
+__device__ __forceinline__ void back(const Front& f, const Intrinsics& k, Acc& acc) {
+    const float x = u2f(f.pk & 0xFFFu), y = u2f((f.pk >> 12) & 0xFFFu);
+    const float gu = f.live ? s16_2f(f.gr & 0xFFFFu) : 0.0f, gv = f.live ? s16_2f(f.gr >> 16) : 0.0f;
     float J[6];
-    jacobian_at(gu, gv, x, y, rho, k, J);
-    const float a = u - u2f(uint32_t(iu) & 0xFFFu), b = v - u2f(uint32_t(iv) & 0xFFFu);
-    const float val = (1.0f - b) * (1.0f - a) * u2f(t00) + b * (1.0f - a) * u2f(t10) + (1.0f - b) * a * u2f(t01) + b * a * u2f(t11);
-    const float r = inside ? val - u2f(pk >> 24) : 0.0f;
+    jacobian_at(gu, gv, x, y, f.rho, k, J);
+    const float a = f.a, b = f.b;
+    const float val = (1.0f - b) * (1.0f - a) * u2f(f.t00) + b * (1.0f - a) * u2f(f.t10) + (1.0f - b) * a * u2f(f.t01) + b * a * u2f(f.t11);
+    const float r = f.inside ? val - u2f(f.pk >> 24) : 0.0f;
     acc.e = fmaf(r, r, acc.e);
-    acc.n += inside ? 1.0f : 0.0f;
+    acc.n += f.inside ? 1.0f : 0.0f;
 #pragma unroll
     for (int c = 0; c < 6; ++c) acc.g[c] = fmaf(J[c], r, acc.g[c]);
+    // H = H_total - sum over outside candidates of J J^T: only warps that own an outside candidate pay for it
+    const bool outside = f.live && !f.inside;
+    if (__any_sync(0xffffffffu, outside)) {
 #pragma unroll
-    for (int c = 0; c < 6; ++c)
+        for (int c = 0; c < 6; ++c) {
+            const float jc = outside ? J[c] : 0.0f;
 #pragma unroll
-        for (int d = c; d < 6; ++d) acc.h[tri(c, d)] = fmaf(J[c], J[d], acc.h[tri(c, d)]);
+            for (int d = c; d < 6; ++d) acc.h[tri(c, d)] = fmaf(jc, J[d], acc.h[tri(c, d)]);
+        }
+    }
 }
 
 // The serial part of one LM round, run by thread 0 of every CTA of the team on identical inputs.
@@ -245,15 +302,20 @@ __device__ __noinline__ void lm_decide(LmShared& S, const AlignParams& P, const 
 __global__ void __launch_bounds__(kBlock, 2) k_align(const AlignParams P) {
     __shared__ LmShared S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_producer = warp == kWarps;
     const int team = P.team;
     const int team_id = blockIdx.x / team, rank = blockIdx.x - team_id * team;
     const int n_teams = gridDim.x / team;
     TeamScratch* scratch = team > 1 ? P.scratch + team_id : nullptr;
-    unsigned epoch = 0;  // passes this team has synchronised on so far (same in every CTA of the team)
-    uint32_t phase_bits = 0;  // per-warp: parity to wait for next on each ring stage
+    unsigned epoch = 0;      // passes this team has synchronised on so far (same in every CTA of the team)
+    uint32_t ring_count = 0; // chunks this warp has consumed (consumer) / this lane has filled (producer lane w)
+    const uint64_t l2_policy = l2_evict_first_policy();
     if (tid == 0) {
         for (int w = 0; w < kWarps; ++w)
-            for (int st = 0; st < kStages; ++st) mbar_init(smem_u32(&S.full_bar[w][st]), 1);
+            for (int st = 0; st < kStages; ++st) {
+                mbar_init(smem_u32(&S.full_bar[w][st]), 1);
+                mbar_init(smem_u32(&S.empty_bar[w][st]), 1);
+            }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -277,10 +339,10 @@ __global__ void __launch_bounds__(kBlock, 2) k_align(const AlignParams P) {
             const int wm2i = lj.cols - 2, hm2i = rows - 2;
             const float wm2 = float(wm2i), hm2 = float(hm2i);
             const Intrinsics k = lj.k;
-            const uint32_t* __restrict__ pk = lj.pk;
-            const float* __restrict__ idp = lj.idepth;
-            const uint32_t* __restrict__ grd = lj.grad;
+            const uint32_t* __restrict__ pts = lj.pts;
             const uint8_t* __restrict__ img = lj.img;
+            const int n_chunks = (n + kChunk - 1) / kChunk;
+            const int TW = team * kWarps;
             if (tid == 0) {
                 S.cand_model = S.out_model;
                 S.init_phase = 1;
@@ -289,75 +351,86 @@ __global__ void __launch_bounds__(kBlock, 2) k_align(const AlignParams P) {
             __syncthreads();
 
             for (;;) {
-                float M[12];
-#pragma unroll
-                for (int c = 0; c < 12; ++c) M[c] = S.M[c];
-                Acc acc;
-                acc.e = 0.0f;
-                acc.n = 0.0f;
-#pragma unroll
-                for (int c = 0; c < 6; ++c) acc.g[c] = 0.0f;
-#pragma unroll
-                for (int c = 0; c < 21; ++c) acc.h[c] = 0.0f;
-
-                // ---- pass: this warp owns chunks gw, gw + TW, ... of kChunk candidates; its ring of kStages
-                // stages is filled by TMA bulk copies (3 x 256 B per stage) that complete on the stage's mbarrier.
-                {
-                    const int n_chunks = (n + kChunk - 1) / kChunk;
-                    const int TW = team * kWarps, gw = rank * kWarps + warp;
-                    float* ring = S.ring[warp];
-                    auto fill = [&](int stage, int chunk) {  // lane 0 only
-                        const uint32_t bar = smem_u32(&S.full_bar[warp][stage]);
-                        const uint32_t dst = smem_u32(ring + stage * kStageWords);
-                        const size_t e0 = size_t(chunk) * kChunk;
-                        mbar_expect_tx(bar, 3 * kChunkBytes);
-                        bulk_g2s(dst, pk + e0, kChunkBytes, bar);
-                        bulk_g2s(dst + kChunkBytes, idp + e0, kChunkBytes, bar);
-                        bulk_g2s(dst + 2 * kChunkBytes, grd + e0, kChunkBytes, bar);
-                    };
-                    if (lane == 0) {
-#pragma unroll
-                        for (int st = 0; st < kStages; ++st)
-                            if (gw + st * TW < n_chunks) fill(st, gw + st * TW);
+                float vals[kNumAcc];
+                if (is_producer) {
+                    // ---- producer warp: lane w feeds consumer warp w's ring (chunks gw, gw + TW, ...) with one 768-byte
+                    // bulk copy per stage; lanes poll their consumer's empty barrier without blocking each other
+                    {
+                        int c = rank * kWarps + lane;
+                        bool active = lane < kWarps && c < n_chunks;
+                        while (__any_sync(0xffffffffu, active)) {
+                            bool did = false;
+                            if (active) {
+                                const uint32_t stage = ring_count % kStages, use = ring_count / kStages;
+                                if (mbar_test(smem_u32(&S.empty_bar[lane][stage]), (use & 1u) ^ 1u)) {  // stage drained
+                                    const uint32_t bar = smem_u32(&S.full_bar[lane][stage]);
+                                    mbar_expect_tx(bar, kStageBytes);
+                                    bulk_g2s(smem_u32(&S.ring[lane][stage * kStageWords]), pts + size_t(c) * kStageWords, kStageBytes, bar,
+                                             l2_policy);
+                                    ++ring_count;
+                                    c += TW;
+                                    active = c < n_chunks;
+                                    did = true;
+                                }
+                            }
+                            if (!__any_sync(0xffffffffu, did)) __nanosleep(64);
+                        }
                     }
-                    int stage = 0;
+#pragma unroll
+                    for (int c = 0; c < kNumAcc; ++c) vals[c] = 0.0f;
+                } else {
+                    // ---- consumer warps: two candidates per lane per stage
+                    float M[12];
+#pragma unroll
+                    for (int c = 0; c < 12; ++c) M[c] = S.M[c];
+                    Acc acc;
+                    acc.e = 0.0f;
+                    acc.n = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) acc.g[c] = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < 21; ++c) acc.h[c] = 0.0f;
+                    const int gw = rank * kWarps + warp;
+                    // software pipeline over candidates: front(q+1) is issued before back(q)
+                    Front fx, fy;
+                    fy.pk = 0u; fy.gr = 0u; fy.rho = 1.0f; fy.a = 0.0f; fy.b = 0.0f;
+                    fy.t00 = fy.t10 = fy.t01 = fy.t11 = 0u;
+                    fy.live = false; fy.inside = false;
                     for (int c = gw; c < n_chunks; c += TW) {
-                        mbar_wait(smem_u32(&S.full_bar[warp][stage]), (phase_bits >> stage) & 1u);
-                        phase_bits ^= 1u << stage;
-                        const float* sp = ring + stage * kStageWords;
+                        const uint32_t stage = ring_count % kStages, use = ring_count / kStages;
+                        mbar_wait(smem_u32(&S.full_bar[warp][stage]), use & 1u);  // TMA bytes have landed
+                        const float* sp = &S.ring[warp][stage * kStageWords];
                         const uint32_t pk0 = __float_as_uint(sp[lane]), pk1 = __float_as_uint(sp[lane + 32]);
                         const float rho0 = sp[kChunk + lane], rho1 = sp[kChunk + lane + 32];
                         const uint32_t gr0 = __float_as_uint(sp[2 * kChunk + lane]), gr1 = __float_as_uint(sp[2 * kChunk + lane + 32]);
                         __syncwarp();
-                        if (lane == 0 && c + kStages * TW < n_chunks) {
-                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // order our reads before the refill
-                            fill(stage, c + kStages * TW);
-                        }
+                        if (lane == 0) mbar_arrive(smem_u32(&S.empty_bar[warp][stage]));  // hand the stage back
+                        ++ring_count;
                         const int i0 = c * kChunk + lane;
-                        eval_point(i0 < n, pk0, rho0, gr0, M, k, &S.cand_model, img, rows, wm2i, hm2i, wm2, hm2, acc);
-                        eval_point(i0 + 32 < n, pk1, rho1, gr1, M, k, &S.cand_model, img, rows, wm2i, hm2i, wm2, hm2, acc);
-                        stage = (stage + 1 == kStages) ? 0 : stage + 1;
+                        front(i0 < n, pk0, rho0, gr0, M, k, &S.cand_model, img, rows, wm2i, hm2i, wm2, hm2, fx);
+                        back(fy, k, acc);
+                        front(i0 + 32 < n, pk1, rho1, gr1, M, k, &S.cand_model, img, rows, wm2i, hm2i, wm2, hm2, fy);
+                        back(fx, k, acc);
                     }
-                }
-
-                // ---- reduce: warp shuffle, then per-CTA f64 sums in fixed order
-                float vals[kNumAcc];
-                vals[0] = acc.e;
-                vals[1] = acc.n;
+                    back(fy, k, acc);
+                    vals[0] = acc.e;
+                    vals[1] = acc.n;
 #pragma unroll
-                for (int c = 0; c < 6; ++c) vals[2 + c] = acc.g[c];
+                    for (int c = 0; c < 6; ++c) vals[2 + c] = acc.g[c];
 #pragma unroll
-                for (int c = 0; c < 21; ++c) vals[8 + c] = acc.h[c];
+                    for (int c = 0; c < 21; ++c) vals[8 + c] = acc.h[c];
+                    // ---- reduce: warp shuffle, then per-CTA f64 sums in fixed order
 #pragma unroll
-                for (int c = 0; c < kNumAcc; ++c) {
-                    float v = vals[c];
+                    for (int c = 0; c < kNumAcc; ++c) {
+                        float v = vals[c];
 #pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-                    vals[c] = v;
-                }
-                if (lane == 0) {
+                        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                        vals[c] = v;
+                    }
+                    if (lane == 0) {
 #pragma unroll
-                    for (int c = 0; c < kNumAcc; ++c) S.warp_part[warp][c] = vals[c];
+                        for (int c = 0; c < kNumAcc; ++c) S.warp_part[warp][c] = vals[c];
+                    }
                 }
                 __syncthreads();
                 if (tid < kNumAcc) {
@@ -387,6 +460,10 @@ __global__ void __launch_bounds__(kBlock, 2) k_align(const AlignParams P) {
                         S.tot[tid] = s;
                     }
                 }
+                __syncthreads();
+                // H over the inside set = H_total (all candidates, per keyframe level) - H_outside; an empty inside
+                // set must give an exactly zero H (the reference then fails its Cholesky, lm_optimizer.rs:131-133)
+                if (tid >= 8 && tid < kNumAcc) S.tot[tid] = S.tot[1] > 0.0 ? lj.h_total[tid - 8] - S.tot[tid] : 0.0;
                 __syncthreads();
 
                 // ---- decide + step (serial, redundantly identical in every CTA of the team)
@@ -432,11 +509,11 @@ __global__ void __launch_bounds__(kBlock, 2) k_align(const AlignParams P) {
             const int n = *lj.n_ptr;
             if (tid == 0) warp_matrix(S.out_model, lj.k, S.M);
             __syncthreads();
-            float s = 0.0f;
-            if (rank == 0) {
-                for (int i = tid; i < n; i += kBlock) {
-                    const uint32_t p = lj.pk[i];
-                    const float rho = lj.idepth[i];
+            if (rank == 0 && !is_producer) {
+                float s = 0.0f;
+                for (int i = tid; i < n; i += kConsumers) {
+                    const uint32_t p = lj.pts[pt_word(i, 0)];
+                    const float rho = __uint_as_float(lj.pts[pt_word(i, 1)]);
                     const float x = float(p & 0xFFFu), y = float((p >> 12) & 0xFFFu);
                     const float U = fmaf(S.M[0], x, fmaf(S.M[1], y, fmaf(S.M[3], rho, S.M[2])));
                     const float V = fmaf(S.M[4], x, fmaf(S.M[5], y, fmaf(S.M[7], rho, S.M[6])));

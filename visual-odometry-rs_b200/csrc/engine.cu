@@ -89,11 +89,10 @@ class Engine {
     uint8_t* d_mask = nullptr;       // coarse-to-fine masks of all levels
     float* d_idepth = nullptr;       // idepth pyramid maps (NaN = unknown)
     float* d_weight = nullptr;
-    uint32_t* d_pk = nullptr;        // candidate streams
-    float* d_pt_idepth = nullptr;
-    uint32_t* d_pt_grad = nullptr;
+    uint32_t* d_pts = nullptr;       // chunk-blocked candidates, 3 * pt_total words per stream
     int* d_blk_count = nullptr;
     int* d_n_points = nullptr;       // [n][kMaxLevels]
+    double* d_h_total = nullptr;     // [n][kMaxLevels][kHStride]
     int* d_items = nullptr;
     AlignJob* d_jobs = nullptr;
     Pose* d_init = nullptr;
@@ -122,8 +121,8 @@ class Engine {
             cudaSetDevice(device);
             cudaStreamSynchronize(L.stream);
         }
-        void* dev_ptrs[] = {d_pyr, d_stage8, d_stage16, d_depth, d_grad, d_g2, d_mask, d_idepth, d_weight, d_pk, d_pt_idepth,
-                            d_pt_grad, d_blk_count, d_n_points, d_items, d_jobs, d_init, d_results, d_scratch, d_trace, d_tmp};
+        void* dev_ptrs[] = {d_pyr, d_stage8, d_stage16, d_depth, d_grad, d_g2, d_mask, d_idepth, d_weight, d_pts,
+                            d_blk_count, d_n_points, d_h_total, d_items, d_jobs, d_init, d_results, d_scratch, d_trace, d_tmp};
         for (void* p : dev_ptrs)
             if (p) cudaFree(p);
         void* host_ptrs[] = {h_init, h_results, h_items, h_n_points, h_jobs};
@@ -204,15 +203,13 @@ class Engine {
         CU_TRY(cudaMalloc(&d_mask, N * P));
         CU_TRY(cudaMalloc(&d_idepth, N * P * 4));
         CU_TRY(cudaMalloc(&d_weight, N * P * 4));
-        CU_TRY(cudaMalloc(&d_pk, N * PT * 4));
-        CU_TRY(cudaMalloc(&d_pt_idepth, N * PT * 4));
-        CU_TRY(cudaMalloc(&d_pt_grad, N * PT * 4));
-        // bulk copies of a partial last chunk read up to 15 B past the last candidate: keep it initialised
-        CU_TRY(cudaMemsetAsync(d_pk, 0, N * PT * 4, L.stream));
-        CU_TRY(cudaMemsetAsync(d_pt_idepth, 0, N * PT * 4, L.stream));
-        CU_TRY(cudaMemsetAsync(d_pt_grad, 0, N * PT * 4, L.stream));
+        CU_TRY(cudaMalloc(&d_pts, N * PT * 12));
+        // a partial last chunk is staged whole: keep its padding initialised
+        CU_TRY(cudaMemsetAsync(d_pts, 0, N * PT * 12, L.stream));
         CU_TRY(cudaMalloc(&d_blk_count, N * size_t(g.blk_total) * 4));
         CU_TRY(cudaMalloc(&d_n_points, N * kMaxLevels * 4));
+        CU_TRY(cudaMalloc(&d_h_total, N * kMaxLevels * kHStride * sizeof(double)));
+        CU_TRY(cudaMemsetAsync(d_h_total, 0, N * kMaxLevels * kHStride * sizeof(double), L.stream));
         CU_TRY(cudaMalloc(&d_items, N * 4));
         CU_TRY(cudaMalloc(&d_jobs, N * sizeof(AlignJob)));
         CU_TRY(cudaMalloc(&d_init, N * sizeof(Pose)));
@@ -242,11 +239,10 @@ class Engine {
         const size_t pbase = size_t(stream) * g.pt_total;
         for (int l = 0; l < g.L; ++l) {
             LevelJob& lj = j.lv[l];
-            lj.pk = d_pk + pbase + g.pt_off[l];
-            lj.idepth = d_pt_idepth + pbase + g.pt_off[l];
-            lj.grad = d_pt_grad + pbase + g.pt_off[l];
+            lj.pts = d_pts + 3 * (pbase + g.pt_off[l]);
             lj.img = d_pyr + base + g.off[l];
             lj.n_ptr = d_n_points + stream * kMaxLevels + l;
+            lj.h_total = d_h_total + (size_t(stream) * kMaxLevels + l) * kHStride;
             lj.rows = g.rows[l];
             lj.cols = g.cols[l];
             lj.k = intr[l];
@@ -311,7 +307,8 @@ class Engine {
         // a 1-level coarse-to-fine pyramid selects every pixel (coarse_to_fine.rs:19-21)
         launch_idepth(L, g, depth_slab, size_t(rows) * cols, d_mask, dense || g.L == 1, cfg.depth_scale, cfg.idepth_variance, d_idepth,
                       d_weight, d_items, m);
-        launch_compact(L, g, d_idepth, d_pyr, d_grad, d_blk_count, d_n_points, d_pk, d_pt_idepth, d_pt_grad, d_items, m);
+        launch_compact(L, g, d_idepth, d_pyr, d_grad, d_blk_count, d_n_points, d_pts, d_items, m);
+        launch_h_total(L, g, intr, d_pts, d_n_points, d_h_total, d_items, m);
         CU_TRY(cudaGetLastError());
         CU_TRY(cudaMemcpyAsync(h_n_points, d_n_points, size_t(n) * kMaxLevels * 4, cudaMemcpyDeviceToHost, L.stream));
         return VORS_OK;
@@ -846,12 +843,15 @@ int vors_keyframe_points(const vors_keyframe* kf, uint32_t level, uint32_t* xy, 
     const int np = e->h_n_points[level];
     if (np == 0) return VORS_OK;
     CU_TRY(cudaSetDevice(e->device));
-    const size_t off = size_t(e->g.pt_off[level]);
     const size_t cnt = size_t(np);
-    std::vector<uint32_t> pk(cnt), gr(cnt);
-    CU_TRY(cudaMemcpy(pk.data(), e->d_pk + off, size_t(np) * 4, cudaMemcpyDeviceToHost));
-    CU_TRY(cudaMemcpy(gr.data(), e->d_pt_grad + off, size_t(np) * 4, cudaMemcpyDeviceToHost));
-    if (idepth) CU_TRY(cudaMemcpy(idepth, e->d_pt_idepth + off, size_t(np) * 4, cudaMemcpyDeviceToHost));
+    const size_t words = (cnt + kChunk - 1) / kChunk * (3 * kChunk);
+    std::vector<uint32_t> blk(words), pk(cnt), gr(cnt);
+    CU_TRY(cudaMemcpy(blk.data(), e->d_pts + 3 * size_t(e->g.pt_off[level]), words * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < np; ++i) {
+        pk[size_t(i)] = blk[pt_word(i, 0)];
+        gr[size_t(i)] = blk[pt_word(i, 2)];
+        if (idepth) std::memcpy(&idepth[i], &blk[pt_word(i, 1)], 4);
+    }
     for (int i = 0; i < np; ++i) {
         if (xy) {
             xy[2 * i] = pk[size_t(i)] & 0xFFFu;
@@ -874,8 +874,7 @@ int vors_keyframe_jacobians(const vors_keyframe* kf, uint32_t level, float* jac6
     CU_TRY(cudaSetDevice(e->device));
     int rc = e->need_tmp(size_t(np) * 24);
     if (rc != VORS_OK) return rc;
-    const size_t off = size_t(e->g.pt_off[level]);
-    launch_jacobians(e->L, e->d_pk + off, e->d_pt_idepth + off, e->d_pt_grad + off, np, e->intr[level], e->d_tmp);
+    launch_jacobians(e->L, e->d_pts + 3 * size_t(e->g.pt_off[level]), np, e->intr[level], e->d_tmp);
     CU_TRY(cudaMemcpyAsync(jac6, e->d_tmp, size_t(np) * 24, cudaMemcpyDeviceToHost, e->L.stream));
     CU_TRY(cudaStreamSynchronize(e->L.stream));
     return VORS_OK;

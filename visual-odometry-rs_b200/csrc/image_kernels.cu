@@ -269,9 +269,7 @@ __global__ void __launch_bounds__(1024) k_compact_scan(const Geom g, int* __rest
 __global__ void __launch_bounds__(kCompactBlock) k_compact_scatter(const Geom g, const float* __restrict__ idepth_slab,
                                                                    const uint8_t* __restrict__ pyr_slab,
                                                                    const uint32_t* __restrict__ grad_slab,
-                                                                   const int* __restrict__ blk_base, uint32_t* __restrict__ pk_slab,
-                                                                   float* __restrict__ pt_idepth_slab,
-                                                                   uint32_t* __restrict__ pt_grad_slab,
+                                                                   const int* __restrict__ blk_base, uint32_t* __restrict__ pts_slab,
                                                                    const int* __restrict__ items) {
     __shared__ int warp_cnt[32];
     const int it = item_of(items, blockIdx.y);
@@ -306,24 +304,70 @@ __global__ void __launch_bounds__(kCompactBlock) k_compact_scatter(const Geom g,
     if (known) {
         const int pos = blk_base[size_t(it) * g.blk_total + blk] + warp_cnt[w] + __popc(ballot & ((1u << lane) - 1u));
         const int x = i / R, y = i - x * R;
-        const size_t dst = size_t(it) * g.pt_total + g.pt_off[l] + pos;
-        pk_slab[dst] = uint32_t(x) | (uint32_t(y) << 12) | (uint32_t(pyr_slab[src]) << 24);
-        pt_idepth_slab[dst] = d;
-        pt_grad_slab[dst] = grad_slab[src];
+        uint32_t* lvl = pts_slab + 3 * (size_t(it) * g.pt_total + g.pt_off[l]);
+        lvl[pt_word(pos, 0)] = uint32_t(x) | (uint32_t(y) << 12) | (uint32_t(pyr_slab[src]) << 24);
+        lvl[pt_word(pos, 1)] = __float_as_uint(d);
+        lvl[pt_word(pos, 2)] = grad_slab[src];
     }
 }
 
 }  // namespace
 
 namespace {
-__global__ void k_jacobians(const uint32_t* __restrict__ pk, const float* __restrict__ idepth, const uint32_t* __restrict__ grad,
-                            int n, Intrinsics k, float* __restrict__ out6) {
+struct LevelIntrinsics {
+    Intrinsics k[kMaxLevels];
+};
+
+// Sum over ALL candidates of a level of J J^T (21 unique entries), once per keyframe.  The align kernel then
+// only accumulates J J^T for the candidates that fall OUTSIDE the frame in a pass and forms
+// H = H_total - H_outside (compute_eval_data's `hessian += hes`, lm_optimizer.rs:100, over the inside set).
+// Products are rounded in f32 exactly like the align kernel's, summed in f64 in a fixed order (one CTA per
+// (level, stream), strided assignment, shuffle + shared-memory tree) -> deterministic.
+__global__ void __launch_bounds__(512) k_h_total(const Geom g, const LevelIntrinsics li, const uint32_t* __restrict__ pts_slab,
+                                                 const int* __restrict__ n_points, double* __restrict__ h_total,
+                                                 const int* __restrict__ items) {
+    __shared__ double part[16][21];
+    const int it = item_of(items, blockIdx.y), l = blockIdx.x;
+    const uint32_t* lvl = pts_slab + 3 * (size_t(it) * g.pt_total + g.pt_off[l]);
+    const int n = n_points[it * kMaxLevels + l];
+    const Intrinsics k = li.k[l];
+    double acc[21];
+#pragma unroll
+    for (int c = 0; c < 21; ++c) acc[c] = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t p = lvl[pt_word(i, 0)], gr = lvl[pt_word(i, 2)];
+        float J[6];
+        jacobian_at(float(int16_t(gr & 0xFFFFu)), float(int16_t(gr >> 16)), float(p & 0xFFFu), float((p >> 12) & 0xFFFu),
+                    __uint_as_float(lvl[pt_word(i, 1)]), k, J);
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = a; b < 6; ++b, ++t) acc[t] += double(J[a]) * double(J[b]);  // exact in f64
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < 21; ++c) {
+        double v = acc[c];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if (lane == 0) part[w][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 21) {
+        double s = 0.0;
+        for (int ww = 0; ww < int(blockDim.x >> 5); ++ww) s += part[ww][threadIdx.x];
+        h_total[(size_t(it) * kMaxLevels + l) * kHStride + threadIdx.x] = s;
+    }
+}
+
+__global__ void k_jacobians(const uint32_t* __restrict__ lvl, int n, Intrinsics k, float* __restrict__ out6) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t p = pk[i], gr = grad[i];
+    const uint32_t p = lvl[pt_word(i, 0)], gr = lvl[pt_word(i, 2)];
     float J[6];
-    jacobian_at(float(int16_t(gr & 0xFFFFu)), float(int16_t(gr >> 16)), float(p & 0xFFFu), float((p >> 12) & 0xFFFu), idepth[i], k,
-                J);
+    jacobian_at(float(int16_t(gr & 0xFFFFu)), float(int16_t(gr >> 16)), float(p & 0xFFFu), float((p >> 12) & 0xFFFu),
+                __uint_as_float(lvl[pt_word(i, 1)]), k, J);
 #pragma unroll
     for (int a = 0; a < 6; ++a) out6[size_t(i) * 6 + a] = J[a];
 }
@@ -392,19 +436,25 @@ void launch_idepth(Launcher& L, const Geom& g, const uint16_t* depth_slab, size_
     }
 }
 void launch_compact(Launcher& L, const Geom& g, const float* idepth_slab, const uint8_t* pyr_slab, const uint32_t* grad_slab,
-                    int* blk_count, int* n_points, uint32_t* pk_slab, float* pt_idepth_slab, uint32_t* pt_grad_slab,
-                    const int* items, int m) {
+                    int* blk_count, int* n_points, uint32_t* pts_slab, const int* items, int m) {
     dim3 gridb(g.blk_total, m);
     k_compact_count<<<gridb, kCompactBlock, 0, L.stream>>>(g, idepth_slab, blk_count, items);
     dim3 grids(g.L, m);
     k_compact_scan<<<grids, 1024, 0, L.stream>>>(g, blk_count, n_points, items);
-    k_compact_scatter<<<gridb, kCompactBlock, 0, L.stream>>>(g, idepth_slab, pyr_slab, grad_slab, blk_count, pk_slab,
-                                                             pt_idepth_slab, pt_grad_slab, items);
+    k_compact_scatter<<<gridb, kCompactBlock, 0, L.stream>>>(g, idepth_slab, pyr_slab, grad_slab, blk_count, pts_slab, items);
     L.launches += 3;
 }
-void launch_jacobians(Launcher& L, const uint32_t* pk, const float* idepth, const uint32_t* grad, int n, Intrinsics k, float* out6) {
+void launch_h_total(Launcher& L, const Geom& g, const Intrinsics* intr, const uint32_t* pts_slab, const int* n_points,
+                    double* h_total, const int* items, int m) {
+    LevelIntrinsics li;
+    for (int l = 0; l < kMaxLevels; ++l) li.k[l] = intr[l < g.L ? l : g.L - 1];
+    dim3 grid(g.L, m);
+    k_h_total<<<grid, 512, 0, L.stream>>>(g, li, pts_slab, n_points, h_total, items);
+    ++L.launches;
+}
+void launch_jacobians(Launcher& L, const uint32_t* pts_level, int n, Intrinsics k, float* out6) {
     if (n <= 0) return;
-    k_jacobians<<<(n + 255) / 256, 256, 0, L.stream>>>(pk, idepth, grad, n, k, out6);
+    k_jacobians<<<(n + 255) / 256, 256, 0, L.stream>>>(pts_level, n, k, out6);
     ++L.launches;
 }
 void launch_se3_exp(Launcher& L, const float* xi6, Pose* out) {

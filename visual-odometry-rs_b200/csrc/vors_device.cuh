@@ -22,6 +22,7 @@ constexpr int kCompactBlock = 1024;  // elements per ordered-compaction block
 constexpr int kTraceCap = 256;       // trace records kept per alignment
 constexpr int kMaxTeam = 160;        // CTAs cooperating on one alignment (<= one per SM)
 constexpr int kChunk = 64;          // candidates per warp-stage of the align kernel's TMA ring (256 B per stream)
+constexpr int kHStride = 24;         // doubles per (stream, level) in the H_total table (21 used)
 constexpr int kNumAcc = 29;          // sum r^2, n_inside, g[6], H[21] (upper triangle)
 
 struct Geom {
@@ -36,12 +37,14 @@ struct Geom {
 };
 
 // One pyramid level of one alignment, as the align kernel sees it.
+// word index of field f (0 pk, 1 idepth, 2 grad) of candidate i inside a level's chunk-blocked block
+__host__ __device__ __forceinline__ size_t pt_word(int i, int f) { return size_t(i / kChunk) * (3 * kChunk) + size_t(f) * kChunk + size_t(i % kChunk); }
+
 struct LevelJob {
-    const uint32_t* pk;
-    const float* idepth;
-    const uint32_t* grad;
+    const uint32_t* pts;  // chunk-blocked candidates of this level
     const uint8_t* img;  // current frame, this level
     const int* n_ptr;    // number of candidates (device memory: written by the compaction kernels)
+    const double* h_total;  // sum over ALL candidates of J J^T, 21 upper-triangle entries (k_h_total)
     int rows, cols;
     Intrinsics k;
 };
@@ -129,10 +132,10 @@ void launch_c2f(Launcher& L, const Geom& g, uint16_t thresh, const uint16_t* g2_
 void launch_idepth(Launcher& L, const Geom& g, const uint16_t* depth_slab, size_t depth_stride, const uint8_t* mask_slab,
                    int dense, float scale, float variance, float* idepth_slab, float* weight_slab, const int* items, int m);
 void launch_compact(Launcher& L, const Geom& g, const float* idepth_slab, const uint8_t* pyr_slab, const uint32_t* grad_slab,
-                    int* blk_count, int* n_points, uint32_t* pk_slab, float* pt_idepth_slab, uint32_t* pt_grad_slab,
-                    const int* items, int m);
-void launch_jacobians(Launcher& L, const uint32_t* pk, const float* idepth, const uint32_t* grad, int n, Intrinsics k,
-                      float* out6);
+                    int* blk_count, int* n_points, uint32_t* pts_slab, const int* items, int m);
+void launch_h_total(Launcher& L, const Geom& g, const Intrinsics* intr, const uint32_t* pts_slab, const int* n_points,
+                    double* h_total, const int* items, int m);
+void launch_jacobians(Launcher& L, const uint32_t* pts_level, int n, Intrinsics k, float* out6);
 void launch_se3_exp(Launcher& L, const float* xi6, Pose* out);
 
 // ---- implemented in align_kernel.cu ---------------------------------------------------------------
