@@ -106,9 +106,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     } while (!done);
 }
 
-// int -> float without the XU pipe: 0x4B000000 | v is the float 2^23 + v for v < 2^23.
-__device__ __forceinline__ float u2f(uint32_t v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }
-__device__ __forceinline__ float s16_2f(uint32_t v16) { return __uint_as_float(0x4B000000u | (v16 ^ 0x8000u)) - 8421376.0f; }
+// int -> float conversions: I2F on the XU pipe (measured: the ALU pipe is the busier one in this kernel, so the
+// 2-ALU-op magic-number conversion is only used where it fuses with work that is needed anyway).
+__device__ __forceinline__ float u2f(uint32_t v) { return float(v); }
+__device__ __forceinline__ float s16_2f(uint32_t v16) { return float(int(short(v16))); }
 __device__ __forceinline__ float rcp_approx(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -163,7 +164,7 @@ constexpr float kBandPx = 1.0f / 128.0f;
 // candidate q+1 before the back of candidate q, so texel latency (L1 miss -> L2) hides behind ~170 instructions.
 struct Front {
     uint32_t pk, gr;
-    float rho, a, b;
+    float x, y, rho, a, b;
     uint32_t t00, t10, t01, t11;
     bool live, inside;
 };
@@ -200,17 +201,19 @@ __device__ __forceinline__ void front(bool live, uint32_t pk, float rho, uint32_
     f.b = v - u2f(uint32_t(iv) & 0xFFFu);
     f.pk = pk;
     f.gr = gr;
+    f.x = x;
+    f.y = y;
     f.rho = rho;
     f.live = live;
     f.inside = inside;
 }
 
 // back: Jacobian, bilinear sample, residual, accumulate.
+template <bool kSkew>
 __device__ __forceinline__ void back(const Front& f, const Intrinsics& k, Acc& acc) {
-    const float x = u2f(f.pk & 0xFFFu), y = u2f((f.pk >> 12) & 0xFFFu);
     const float gu = f.live ? s16_2f(f.gr & 0xFFFFu) : 0.0f, gv = f.live ? s16_2f(f.gr >> 16) : 0.0f;
     float J[6];
-    jacobian_at(gu, gv, x, y, f.rho, k, J);
+    jacobian_at<kSkew>(gu, gv, f.x, f.y, f.rho, k, J);
     const float a = f.a, b = f.b;
     const float val = (1.0f - b) * (1.0f - a) * u2f(f.t00) + b * (1.0f - a) * u2f(f.t10) + (1.0f - b) * a * u2f(f.t01) + b * a * u2f(f.t11);
     const float r = f.inside ? val - u2f(f.pk >> 24) : 0.0f;
@@ -299,6 +302,7 @@ __device__ __noinline__ void lm_decide(LmShared& S, const AlignParams& P, const 
     S.cont = 1;
 }
 
+template <bool kSkew>
 __global__ void __launch_bounds__(kBlock, 2) k_align(const AlignParams P) {
     __shared__ LmShared S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -393,7 +397,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_align(const AlignParams P) {
                     const int gw = rank * kWarps + warp;
                     // software pipeline over candidates: front(q+1) is issued before back(q)
                     Front fx, fy;
-                    fy.pk = 0u; fy.gr = 0u; fy.rho = 1.0f; fy.a = 0.0f; fy.b = 0.0f;
+                    fy.pk = 0u; fy.gr = 0u; fy.x = 0.0f; fy.y = 0.0f; fy.rho = 1.0f; fy.a = 0.0f; fy.b = 0.0f;
                     fy.t00 = fy.t10 = fy.t01 = fy.t11 = 0u;
                     fy.live = false; fy.inside = false;
                     for (int c = gw; c < n_chunks; c += TW) {
@@ -408,11 +412,11 @@ __global__ void __launch_bounds__(kBlock, 2) k_align(const AlignParams P) {
                         ++ring_count;
                         const int i0 = c * kChunk + lane;
                         front(i0 < n, pk0, rho0, gr0, M, k, &S.cand_model, img, rows, wm2i, hm2i, wm2, hm2, fx);
-                        back(fy, k, acc);
+                        back<kSkew>(fy, k, acc);
                         front(i0 + 32 < n, pk1, rho1, gr1, M, k, &S.cand_model, img, rows, wm2i, hm2i, wm2, hm2, fy);
-                        back(fx, k, acc);
+                        back<kSkew>(fx, k, acc);
                     }
-                    back(fy, k, acc);
+                    back<kSkew>(fy, k, acc);
                     vals[0] = acc.e;
                     vals[1] = acc.n;
 #pragma unroll
@@ -553,7 +557,7 @@ cudaError_t align_query(AlignLaunchInfo* info) {
     int sms = 0, per_sm = 0;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align, kBlock, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align<true>, kBlock, 0);
     if (e != cudaSuccess) return e;
     info->block = kBlock;
     info->sm_count = sms;
@@ -564,12 +568,16 @@ cudaError_t align_query(AlignLaunchInfo* info) {
 cudaError_t launch_align(Launcher& L, const AlignParams& p, int n_teams) {
     const int grid = n_teams * p.team;
     ++L.launches;
+    const void* fn = p.has_skew ? (const void*)k_align<true> : (const void*)k_align<false>;
     if (p.team > 1) {
         // co-residency of a team's CTAs is required by the counter barrier: cooperative launch checks it
         void* args[] = {(void*)&p};
-        return cudaLaunchCooperativeKernel((const void*)k_align, dim3(grid), dim3(kBlock), args, 0, L.stream);
+        return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kBlock), args, 0, L.stream);
     }
-    k_align<<<grid, kBlock, 0, L.stream>>>(p);
+    if (p.has_skew)
+        k_align<true><<<grid, kBlock, 0, L.stream>>>(p);
+    else
+        k_align<false><<<grid, kBlock, 0, L.stream>>>(p);
     return cudaGetLastError();
 }
 

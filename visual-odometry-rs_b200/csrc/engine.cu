@@ -371,6 +371,7 @@ class Engine {
         p.energy_delta_stop = cfg.energy_delta_stop;
         p.max_iters = int(cfg.max_iters);
         p.fixed_iters = int(cfg.fixed_iters);
+        p.has_skew = cfg.skew != 0.0f ? 1 : 0;
         return p;
     }
 

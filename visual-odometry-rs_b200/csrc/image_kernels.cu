@@ -337,8 +337,8 @@ __global__ void __launch_bounds__(512) k_h_total(const Geom g, const LevelIntrin
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const uint32_t p = lvl[pt_word(i, 0)], gr = lvl[pt_word(i, 2)];
         float J[6];
-        jacobian_at(float(int16_t(gr & 0xFFFFu)), float(int16_t(gr >> 16)), float(p & 0xFFFu), float((p >> 12) & 0xFFFu),
-                    __uint_as_float(lvl[pt_word(i, 1)]), k, J);
+        jacobian_at<true>(float(int16_t(gr & 0xFFFFu)), float(int16_t(gr >> 16)), float(p & 0xFFFu), float((p >> 12) & 0xFFFu),
+                          __uint_as_float(lvl[pt_word(i, 1)]), k, J);
         int t = 0;
 #pragma unroll
         for (int a = 0; a < 6; ++a)
@@ -366,8 +366,8 @@ __global__ void k_jacobians(const uint32_t* __restrict__ lvl, int n, Intrinsics 
     if (i >= n) return;
     const uint32_t p = lvl[pt_word(i, 0)], gr = lvl[pt_word(i, 2)];
     float J[6];
-    jacobian_at(float(int16_t(gr & 0xFFFFu)), float(int16_t(gr >> 16)), float(p & 0xFFFu), float((p >> 12) & 0xFFFu),
-                __uint_as_float(lvl[pt_word(i, 1)]), k, J);
+    jacobian_at<true>(float(int16_t(gr & 0xFFFFu)), float(int16_t(gr >> 16)), float(p & 0xFFFu), float((p >> 12) & 0xFFFu),
+                      __uint_as_float(lvl[pt_word(i, 1)]), k, J);
 #pragma unroll
     for (int a = 0; a < 6; ++a) out6[size_t(i) * 6 + a] = J[a];
 }

@@ -91,24 +91,38 @@ struct AlignParams {
     // LM constants (lm_optimizer.rs:115,157,173,179,186)
     float lm_coef_init, lm_coef_reject_mult, lm_coef_accept_mult, energy_delta_stop;
     int max_iters, fixed_iters;
+    int has_skew;  // 0 selects the zero-skew Jacobian specialisation
 };
 
 // Row J: warp_jacobian_at (inverse_compositional.rs:313-341), used by the align kernel (J is recomputed
-// per pass in registers instead of being stored) and by the jacobian export kernel.  Same expression
-// order as the reference except that `c / fu` is evaluated as c * (1/fu) (loop-invariant reciprocal).
+// per pass in registers instead of being stored), by k_h_total and by the jacobian export kernel.  Same
+// expression order as the reference except that `c / fu` is evaluated as c * (1/fu) (loop-invariant
+// reciprocal).  kSkew = false is the zero-skew specialisation (every intrinsics set the reference ships,
+// src/dataset/tum_rgbd.rs:23-51, has skew 0): algebraically identical, 7 fewer instructions.
+template <bool kSkew = true>
 __device__ __forceinline__ void jacobian_at(float gu, float gv, float u, float v, float rho, const Intrinsics& k, float J[6]) {
     const float a = u - k.cx;
     const float b = v - k.cy;
-    const float c = a * k.fy - k.s * b;
     const float _fv = 1.0f / k.fy;
     const float _fu = 1.0f / k.fx;
-    const float _fuv = 1.0f / (k.fx * k.fy);
-    J[0] = gu * rho * k.fx;
-    J[1] = rho * (gu * k.s + gv * k.fy);
-    J[2] = -rho * (gu * a + gv * b);
-    J[3] = gu * (-a * b * _fv - k.s) + gv * (-b * b * _fv - k.fy);
-    J[4] = gu * (a * c * _fuv + k.fx) + gv * (b * c * _fuv);
-    J[5] = gu * (-k.fx * k.fx * b + k.s * c) * _fuv + gv * (c * _fu);
+    if (kSkew) {
+        const float c = a * k.fy - k.s * b;
+        const float _fuv = 1.0f / (k.fx * k.fy);
+        J[0] = gu * rho * k.fx;
+        J[1] = rho * (gu * k.s + gv * k.fy);
+        J[2] = -rho * (gu * a + gv * b);
+        J[3] = gu * (-a * b * _fv - k.s) + gv * (-b * b * _fv - k.fy);
+        J[4] = gu * (a * c * _fuv + k.fx) + gv * (b * c * _fuv);
+        J[5] = gu * (-k.fx * k.fx * b + k.s * c) * _fuv + gv * (c * _fu);
+    } else {
+        const float bf = b * _fv, af = a * _fu;  // b / fv, a / fu  (c = a fv, c / (fu fv) = a / fu)
+        J[0] = gu * (rho * k.fx);
+        J[1] = gv * (rho * k.fy);
+        J[2] = -rho * (gu * a + gv * b);
+        J[3] = -(gu * (a * bf) + gv * (b * bf + k.fy));
+        J[4] = gu * (a * af + k.fx) + gv * (b * af);
+        J[5] = gv * (a * (k.fy * _fu)) - gu * (b * (k.fx * _fv));
+    }
 }
 
 // ---- launchers implemented in image_kernels.cu -------------------------------------------------
