@@ -178,15 +178,15 @@ def run_ours(args):
     ts = [np.full(B, float(k)) for k in range(T + 1)]
     status = np.zeros(B, np.int32)
     stats = (vb.TrackStats * B)()
-    poses_dev = torch.zeros((B, 7), dtype=torch.float32, device=device)
-    gathered = [torch.zeros_like(poses_dev) for _ in range(world)] if world > 1 else None
+    from vors_b200 import shard
 
     def gather_poses(bt):
-        """Frames shard across ranks with no data-path collective; the only exchange is the pose gather."""
+        """Streams shard across ranks with no data-path collective; the only exchange is this all-gather of 32-byte
+        pose records (NCCL), once per step."""
         if world > 1:
             _, p = bt.current_frames()
-            poses_dev.copy_(torch.from_numpy(p), non_blocking=False)
-            dist.all_gather(gathered, poses_dev)
+            return shard.gather_poses(shard.pack_records(p, status), B * world, device=device)
+        return None
 
     def new_tracker():
         g0 = gray_h[0].numpy()
