@@ -96,6 +96,7 @@ def _load(name: str) -> C.CDLL:
     vp = C.c_void_p
     sig = {
         "ref_config_default": (None, [P(Config)]),
+        "ref_set_accum_f64": (None, [C.c_int]),
         "ref_pyramid_shapes": (C.c_int, [C.c_int, C.c_int, C.c_int, _i32p, _i32p]),
         "ref_mean_pyramid": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, _u8p]),
         "ref_gradient_centered": (None, [_u8p, C.c_int, C.c_int, _i16p, _i16p]),

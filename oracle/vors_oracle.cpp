@@ -627,6 +627,11 @@ std::unique_ptr<Keyframe> precompute_multires_data(const ref_config& cfg, const 
     return kf;
 }
 
+// Test-only switch (ref_set_accum_f64): accumulate energy / gradient / hessian in f64 instead of the reference's
+// sequential f32.  Used to separate "GPU differs from the reference's arithmetic" from "the reference's own
+// sequential-f32 sums are noisy" (they absorb small terms once the running sum passes 2^24..2^25).
+thread_local bool g_accum_f64 = false;
+
 struct EvalData {
     Mat6 hessian;
     Float gradient[6];
@@ -643,6 +648,7 @@ struct Precomputed {
 Precomputed eval_energy(const Keyframe& kf, int lvl, const uint8_t* image, int rows, int cols, const Iso& model) {
     Precomputed pre;
     Float energy_sum = 0.0f;
+    double energy_sum64 = 0.0;
     const auto& coords = kf.coords[lvl];
     const auto& zs = kf.idepth[lvl];
     const Mat<uint8_t>& tmpl = kf.img[lvl];
@@ -654,11 +660,12 @@ Precomputed eval_energy(const Keyframe& kf, int lvl, const uint8_t* image, int r
         if (interpolate(u, v, image, rows, cols, im)) {
             const Float r = im - Float(tmpl(int(y), int(x)));
             energy_sum += r * r;
+            energy_sum64 += double(r) * double(r);
             pre.residuals.push_back(r);
             pre.inside_indices.push_back(uint32_t(idx));
         }
     }
-    pre.energy = energy_sum / Float(pre.residuals.size());
+    pre.energy = g_accum_f64 ? Float(energy_sum64 / double(pre.residuals.size())) : energy_sum / Float(pre.residuals.size());
     return pre;
 }
 
@@ -667,6 +674,22 @@ EvalData compute_eval_data(const Keyframe& kf, int lvl, const Iso& model, const 
     EvalData e;
     std::memset(&e.hessian, 0, sizeof(e.hessian));
     for (int a = 0; a < 6; ++a) e.gradient[a] = 0.0f;
+    if (g_accum_f64) {
+        double gd[6] = {0}, Hd[36] = {0};
+        for (size_t i = 0; i < pre.inside_indices.size(); ++i) {
+            const auto& jac = kf.jac[lvl][pre.inside_indices[i]];
+            const double r = pre.residuals[i];
+            for (int a = 0; a < 6; ++a) gd[a] += double(jac[a]) * r;
+            for (int a = 0; a < 6; ++a)
+                for (int b = 0; b < 6; ++b) Hd[a * 6 + b] += double(jac[a]) * double(jac[b]);
+        }
+        for (int a = 0; a < 6; ++a) e.gradient[a] = Float(gd[a]);
+        for (int a = 0; a < 6; ++a)
+            for (int b = 0; b < 6; ++b) e.hessian.m[a][b] = Float(Hd[a * 6 + b]);
+        e.energy = pre.energy;
+        e.model = model;
+        return e;
+    }
     for (size_t i = 0; i < pre.inside_indices.size(); ++i) {
         const uint32_t idx = pre.inside_indices[i];
         const auto& jac = kf.jac[lvl][idx];
@@ -940,6 +963,8 @@ struct ref_tracker {
 };
 
 extern "C" {
+
+void ref_set_accum_f64(int on) { g_accum_f64 = on != 0; }
 
 void ref_config_default(ref_config* c) {
     std::memset(c, 0, sizeof(*c));

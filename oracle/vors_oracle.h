@@ -84,6 +84,8 @@ typedef struct ref_track_stats {
 } ref_track_stats;
 
 void ref_config_default(ref_config* cfg);
+/* Test-only: 1 = accumulate E / g / H in f64 (calling thread only); 0 = the reference's sequential f32 (default). */
+void ref_set_accum_f64(int on);
 
 /* ---- rows A-D, S: pyramid and gradients ------------------------------------------- */
 int ref_pyramid_shapes(int rows, int cols, int max_levels, int* out_rows, int* out_cols);

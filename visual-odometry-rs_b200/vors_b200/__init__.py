@@ -303,9 +303,9 @@ class BatchTracker:
 
     def current_frames(self):
         ts = np.zeros(self.n, np.float64)
-        poses = (Pose * self.n)()
-        _check(self._lib.vors_batch_current_frames(self._h, _ptr(ts), poses))
-        return ts, np.stack([p.as_array() for p in poses])
+        poses = np.zeros((self.n, 7), np.float32)  # vors_pose is 7 packed floats
+        _check(self._lib.vors_batch_current_frames(self._h, _ptr(ts), _ptr(poses)))
+        return ts, poses
 
     def last_timing(self):
         ms = (C.c_float * 4)()
