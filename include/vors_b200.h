@@ -46,6 +46,7 @@ extern "C" {
 
 #define VORS_CANDIDATES_COARSE_TO_FINE 0 /* reference: src/core/candidates/coarse_to_fine.rs */
 #define VORS_CANDIDATES_DENSE 1          /* extension: every pixel with depth != 0 */
+#define VORS_CANDIDATES_DSO 2            /* extension (BASELINE config 3): src/core/candidates/dso.rs at level 0 */
 
 /* Replaces `track::Config` (src/core/track/inverse_compositional.rs:37-49) plus the constants the
  * reference hard-codes (src/core/track/lm_optimizer.rs:115,157,173,179,186; inverse_compositional.rs:224).
@@ -67,7 +68,7 @@ typedef struct vors_config {
     float keyframe_flow_threshold; /* 1.0 px at the coarsest level */
     int32_t device;                /* CUDA ordinal; -1 = current device */
     uint32_t team_size;            /* CTAs cooperating on one alignment; 0 = auto */
-    uint32_t dso_nb_target;        /* reserved (DSO selector) */
+    uint32_t dso_nb_target;        /* VORS_CANDIDATES_DSO: target number of level-0 candidates (2000) */
     uint32_t reserved[3];
 } vors_config;
 
@@ -189,6 +190,22 @@ int vors_gradients(const uint8_t* img, uint32_t rows, uint32_t cols, uint32_t ma
  * (coarse_to_fine.rs:15-32).  g2_concat finest first; masks_concat (0/1 bytes) finest first. */
 int vors_candidates_coarse_to_fine(uint16_t diff_threshold, const uint16_t* g2_concat, uint32_t rows,
                                    uint32_t cols, uint32_t n_levels, uint8_t* masks_concat);
+
+/* Replaces `candidates::dso::select(&DMatrix<u16>, DEFAULT_REGION_CONFIG, DEFAULT_BLOCK_CONFIG, RecursiveConfig{
+ * nb_iterations_left, ..DEFAULT}, nb_target) -> DMatrix<bool>` (src/core/candidates/dso.rs:98-150).  `gradients` is the
+ * column-major u16 gradient-magnitude map.  The reference's thinning branch draws from thread_rng (dso.rs:140-143,
+ * not reproducible); here the r-th picked pixel (column-major order) uses the r-th output of splitmix64(seed).
+ * Returns the number of block candidates of the last recursion (before thinning) or <0; VORS_E_INVALID also stands
+ * for the reference's `expect("woops")` panic (threshold does not fit u16). */
+int vors_candidates_dso(const uint16_t* gradients, uint32_t rows, uint32_t cols, uint32_t nb_target,
+                        uint32_t nb_iterations_left, uint64_t seed, uint8_t* mask_out, int* used_random_branch);
+
+/* Replaces the example gradient-norm recipe: level 0 `gradient::squared_norm_direct`
+ * (src/core/gradient.rs:49-65), levels >= 1 `multires::gradients_squared_norm` (multires.rs:96-106 with
+ * gradient::bloc_squared_norm, gradient.rs:102-111) — what examples/candidates_coarse-to-fine.rs:55-69 feeds the
+ * selector; numerically different from vors_gradients (no intermediate truncation).  Returns the number of levels. */
+int vors_gradient_norms_example(const uint8_t* img, uint32_t rows, uint32_t cols, uint32_t max_levels,
+                                uint16_t* g2_concat);
 
 /* Replaces `precompute_multires_data` (inverse_compositional.rs:105-161): keyframe precompute. */
 typedef struct vors_keyframe vors_keyframe;

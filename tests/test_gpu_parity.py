@@ -408,3 +408,81 @@ def test_identical_frame_property_full_size(vb, oracle):
     _, pose = t.current_frame()
     assert stats.status == 0 and stats.optical_flow < 1e-2 and stats.keyframe_changed == 0
     _pose_close(pose.as_array(), vb.Pose.identity().as_array(), oracle, 1e-5, 1e-5)
+
+
+# ---- rows R, S: DSO selector and the example gradient-norm recipe ------------------------------------------------
+
+@pytest.mark.parametrize("shape", [(48, 64), (37, 53), (480, 640), (135, 240)])
+def test_example_gradient_norms_bit_exact(vb, oracle, shape):
+    rng = np.random.default_rng(shape[1])
+    for kind in ("noise", "smooth", "extreme"):
+        img = _img(rng, shape, kind)
+        L = len(oracle.pyramid_shapes(*shape, 5))
+        pyr = oracle.mean_pyramid(img, L)
+        cat = np.concatenate([np.ascontiguousarray(p.T).reshape(-1) for p in pyr])
+        ref = np.zeros(cat.size, np.uint16)
+        oracle.lib().ref_gradients_squared_norm_example(cat, shape[0], shape[1], L, ref)
+        got = vb.gradient_norms_example(img, L)
+        assert np.array_equal(np.concatenate([np.ascontiguousarray(g.T).reshape(-1) for g in got]), ref)
+
+
+def _dso_oracle(oracle, mag, nb_target, iters, seed):
+    import ctypes as C
+
+    rows, cols = mag.shape
+    mask = np.zeros(mag.size, np.uint8)
+    used = C.c_int()
+    n = oracle.lib().ref_dso_select(np.ascontiguousarray(mag.T).reshape(-1).astype(np.uint16), rows, cols, nb_target, iters, seed,
+                                    mask, C.byref(used))
+    return mask.reshape(cols, rows).T.astype(bool), n, bool(used.value)
+
+
+@pytest.mark.parametrize("shape,target", [((240, 320), 500), ((480, 640), 2000), ((480, 640), 300), ((133, 211), 150),
+                                          ((960, 1280), 2000), ((480, 640), 20000)])
+def test_dso_select_bit_exact(vb, oracle, shape, target):
+    scene = synth.make_scene(shape[0] + target, *shape)
+    gray, _ = synth.render(scene)
+    g2 = np.zeros(gray.size, np.uint16)
+    oracle.lib().ref_squared_norm_direct(np.ascontiguousarray(gray.T).reshape(-1), shape[0], shape[1], g2)
+    mag = np.sqrt(g2.astype(np.float32)).astype(np.uint16).reshape(shape[1], shape[0]).T  # examples/candidates_dso.rs:42
+    branches = set()
+    for iters in (0, 1, 2):
+        ref_mask, ref_n, ref_used = _dso_oracle(oracle, mag, target, iters, 1234)
+        mask, n, used = vb.candidates_dso(mag, target, iters, 1234)
+        assert n == ref_n and used == ref_used
+        assert np.array_equal(mask, ref_mask), f"{np.count_nonzero(mask != ref_mask)} mask bits differ (iters {iters})"
+        branches.add(ref_used)
+    # adversarial map: flat regions (ties everywhere) and saturated values
+    rng = np.random.default_rng(7)
+    flat = rng.choice(np.array([0, 0, 3, 3, 9, 200, 65535], np.uint16), shape)
+    ref_mask, ref_n, _ = _dso_oracle(oracle, flat, target, 1, 5)
+    if ref_n >= 0:
+        mask, n, _ = vb.candidates_dso(flat, target, 1, 5)
+        assert n == ref_n and np.array_equal(mask, ref_mask)
+    else:
+        with pytest.raises(vb.VorsError):
+            vb.candidates_dso(flat, target, 1, 5)
+
+
+def test_tracker_dso_candidates_config3(vb, oracle):
+    """BASELINE config 3 shape: 1280x960, DSO candidates (~2k at level 0), 6 levels, reference-adaptive LM."""
+    scene, f0, f1, pose1 = synth.make_pair(seed=3000, rows=960, cols=1280)
+    _, _, out = _run_both(vb, oracle, scene, [f0, f1], nb_levels=6, candidate_mode=2, dso_nb_target=2000)
+    stats, trace, (ts, pose), ostats, otrace, (ots, opose) = out[0]
+    assert stats.status == ostats.status == 0
+    assert list(stats.n_points)[:6] == list(ostats.n_points)[:6]
+    assert 500 < stats.n_points[0] < 8000
+    _same_trace(trace, otrace)
+    _pose_close(pose.as_array(), opose.as_array(), oracle)
+
+
+def test_keyframe_dso_mask_matches_oracle(vb, oracle):
+    scene = synth.make_scene(31, 480, 640)
+    gray, depth = synth.render(scene, None, 0, holes=2)
+    cfg, ocfg = _cfgs(vb, oracle, scene, nb_levels=5, candidate_mode=2, dso_nb_target=1500)
+    kf = vb.Keyframe(cfg, depth, gray)
+    okf = oracle.Keyframe(ocfg, depth, gray)
+    assert np.array_equal(kf.mask0(), okf.mask0())
+    for l in range(5):
+        assert kf.n_points(l) == okf.n_points(l)
+        assert np.array_equal(kf.points(l)[0], okf.points(l)[0])

@@ -99,6 +99,9 @@ class Engine {
     AlignResult* d_results = nullptr;
     TeamScratch* d_scratch = nullptr;
     vors_trace_rec* d_trace = nullptr;
+    uint16_t* d_gradmag = nullptr;   // DSO mode: gradient magnitude of level 0 (one stream at a time)
+    uint8_t* d_dso_ws = nullptr;     // DSO mode: selector workspace
+    int* h_dso_flags = nullptr;      // pinned
     float* d_tmp = nullptr;          // small scratch (jacobian export etc.)
     size_t tmp_bytes = 0;
 
@@ -122,10 +125,10 @@ class Engine {
             cudaStreamSynchronize(L.stream);
         }
         void* dev_ptrs[] = {d_pyr, d_stage8, d_stage16, d_depth, d_grad, d_g2, d_mask, d_idepth, d_weight, d_pts,
-                            d_blk_count, d_n_points, d_h_total, d_items, d_jobs, d_init, d_results, d_scratch, d_trace, d_tmp};
+                            d_blk_count, d_n_points, d_h_total, d_items, d_jobs, d_init, d_results, d_scratch, d_trace, d_tmp, d_gradmag, d_dso_ws};
         for (void* p : dev_ptrs)
             if (p) cudaFree(p);
-        void* host_ptrs[] = {h_init, h_results, h_items, h_n_points, h_jobs};
+        void* host_ptrs[] = {h_init, h_results, h_items, h_n_points, h_jobs, h_dso_flags};
         for (void* p : host_ptrs)
             if (p) cudaFreeHost(p);
         for (auto& e : ev)
@@ -140,8 +143,7 @@ class Engine {
         if (layout_ != VORS_COL_MAJOR && layout_ != VORS_ROW_MAJOR) return fail(VORS_E_INVALID, "unknown layout");
         if (c->nb_levels == 0 || c->nb_levels > kMaxLevels) return fail(VORS_E_INVALID, "nb_levels must be in 1..VORS_MAX_LEVELS");
         if (rows_ > 4096 || cols_ > 4096) return fail(VORS_E_INVALID, "images larger than 4096x4096 are not supported");
-        if (c->candidate_mode != VORS_CANDIDATES_COARSE_TO_FINE && c->candidate_mode != VORS_CANDIDATES_DENSE)
-            return fail(VORS_E_INVALID, "unsupported candidate_mode");
+        if (c->candidate_mode > VORS_CANDIDATES_DSO) return fail(VORS_E_INVALID, "unsupported candidate_mode");
         if (c->candidates_diff_threshold > 65535u) return fail(VORS_E_INVALID, "candidates_diff_threshold exceeds u16");
         uint32_t lr[32], lc[32];
         const int levels = pyramid_shapes(rows_, cols_, c->nb_levels, lr, lc);
@@ -218,6 +220,11 @@ class Engine {
         CU_TRY(cudaMalloc(&d_scratch, size_t(scratch_teams) * sizeof(TeamScratch)));
         CU_TRY(cudaMemsetAsync(d_n_points, 0, N * kMaxLevels * 4, L.stream));
         CU_TRY(cudaMemsetAsync(d_results, 0, N * sizeof(AlignResult), L.stream));
+        CU_TRY(cudaMallocHost(&h_dso_flags, 64));
+        if (cfg.candidate_mode == VORS_CANDIDATES_DSO) {
+            CU_TRY(cudaMalloc(&d_gradmag, I * 2));
+            CU_TRY(cudaMalloc(&d_dso_ws, dso_workspace_bytes(rows, cols)));
+        }
         CU_TRY(cudaMallocHost(&h_init, N * sizeof(Pose)));
         CU_TRY(cudaMallocHost(&h_results, N * sizeof(AlignResult)));
         CU_TRY(cudaMallocHost(&h_items, N * 4));
@@ -302,10 +309,24 @@ class Engine {
     // ---- keyframe precompute (inverse_compositional.rs:105-161) for the m streams in d_items --------
     int precompute(const uint16_t* depth_slab, int m) {
         const int dense = cfg.candidate_mode == VORS_CANDIDATES_DENSE;
-        launch_gradients(L, g, d_pyr, d_grad, dense ? nullptr : d_g2, d_items, m);
-        if (!dense && g.L > 1) launch_c2f(L, g, uint16_t(cfg.candidates_diff_threshold), d_g2, d_mask, d_items, m);
+        launch_gradients(L, g, d_pyr, d_grad, (dense || cfg.candidate_mode == VORS_CANDIDATES_DSO) ? nullptr : d_g2, d_items, m);
+        const bool dso = cfg.candidate_mode == VORS_CANDIDATES_DSO;
+        if (dso) {
+            // BASELINE config 3: DSO selection on the level-0 gradient magnitude (examples/candidates_dso.rs:40-60:
+            // sqrt(squared_norm_direct) as u16, nb_iterations_left = 2), one stream at a time (host-driven recursion)
+            for (int j = 0; j < m; ++j) {
+                const int s = h_items[j];
+                launch_sqnorm_direct(L, d_pyr + size_t(s) * g.pix_total, rows, cols, 1, d_gradmag);
+                const int rc = dso_select_device(L, d_gradmag, rows, cols, int(cfg.dso_nb_target ? cfg.dso_nb_target : 2000), 2,
+                                                 0x9E3779B97F4A7C15ull, d_mask + size_t(s) * g.pix_total, d_dso_ws, h_dso_flags,
+                                                 nullptr, nullptr);
+                if (rc != VORS_OK) return fail(rc, "DSO candidate selection failed");
+            }
+        } else if (!dense && g.L > 1) {
+            launch_c2f(L, g, uint16_t(cfg.candidates_diff_threshold), d_g2, d_mask, d_items, m);
+        }
         // a 1-level coarse-to-fine pyramid selects every pixel (coarse_to_fine.rs:19-21)
-        launch_idepth(L, g, depth_slab, size_t(rows) * cols, d_mask, dense || g.L == 1, cfg.depth_scale, cfg.idepth_variance, d_idepth,
+        launch_idepth(L, g, depth_slab, size_t(rows) * cols, d_mask, dense || (g.L == 1 && !dso), cfg.depth_scale, cfg.idepth_variance, d_idepth,
                       d_weight, d_items, m);
         launch_compact(L, g, d_idepth, d_pyr, d_grad, d_blk_count, d_n_points, d_pts, d_items, m);
         launch_h_total(L, g, intr, d_pts, d_n_points, d_h_total, d_items, m);
@@ -812,6 +833,60 @@ int vors_candidates_coarse_to_fine(uint16_t diff_threshold, const uint16_t* g2_c
     return rc;
 }
 
+int vors_candidates_dso(const uint16_t* gradients, uint32_t rows, uint32_t cols, uint32_t nb_target, uint32_t nb_iterations_left,
+                        uint64_t seed, uint8_t* mask_out, int* used_random_branch) {
+    if (!gradients || !mask_out || nb_target == 0) return fail(VORS_E_INVALID, "null argument");
+    Engine* e = nullptr;
+    int rc = image_engine(rows, cols, 1, &e);
+    if (rc != VORS_OK) return rc;
+    const size_t px = size_t(rows) * cols;
+    uint16_t* d_g = nullptr;
+    uint8_t* ws = nullptr;
+    int nb = 0;
+    cudaError_t ce = cudaMalloc(&d_g, px * 2);
+    if (ce == cudaSuccess) ce = cudaMalloc(&ws, dso_workspace_bytes(int(rows), int(cols)));
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_g, gradients, px * 2, cudaMemcpyHostToDevice, e->L.stream);
+    if (ce != cudaSuccess) {
+        rc = fail(VORS_E_CUDA, "vors_candidates_dso", cudaGetErrorString(ce));
+    } else {
+        rc = dso_select_device(e->L, d_g, int(rows), int(cols), int(nb_target), int(nb_iterations_left), seed, e->d_mask, ws,
+                               e->h_dso_flags, used_random_branch, &nb);
+        if (rc == VORS_OK) {
+            ce = cudaMemcpyAsync(mask_out, e->d_mask, px, cudaMemcpyDeviceToHost, e->L.stream);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->L.stream);
+            if (ce != cudaSuccess) rc = fail(VORS_E_CUDA, "vors_candidates_dso", cudaGetErrorString(ce));
+        } else {
+            fail(rc, rc == VORS_E_INVALID ? "DSO threshold does not fit u16 (the reference panics here) or too many regions" : "CUDA error in DSO selection");
+        }
+    }
+    cudaStreamSynchronize(e->L.stream);
+    if (d_g) cudaFree(d_g);
+    if (ws) cudaFree(ws);
+    delete e;
+    return rc == VORS_OK ? nb : rc;
+}
+
+int vors_gradient_norms_example(const uint8_t* img, uint32_t rows, uint32_t cols, uint32_t max_levels, uint16_t* g2_concat) {
+    if (!img || !g2_concat) return fail(VORS_E_INVALID, "null argument");
+    Engine* e = nullptr;
+    int rc = image_engine(rows, cols, max_levels, &e);
+    if (rc != VORS_OK) return rc;
+    const uint8_t* one[1] = {img};
+    rc = e->upload_images_host(one);
+    const int levels = e->g.L;
+    if (rc == VORS_OK) {
+        launch_pyramid(e->L, e->g, e->d_pyr, nullptr, 1);
+        launch_sqnorm_direct(e->L, e->d_pyr, e->g.rows[0], e->g.cols[0], 0, e->d_g2);
+        for (int l = 1; l < levels; ++l)
+            launch_bloc_sqnorm(e->L, e->d_pyr + e->g.off[l - 1], e->g.rows[l - 1], e->g.rows[l], e->g.cols[l], e->d_g2 + e->g.off[l]);
+        cudaError_t ce = cudaMemcpyAsync(g2_concat, e->d_g2, size_t(e->g.pix_total) * 2, cudaMemcpyDeviceToHost, e->L.stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->L.stream);
+        if (ce != cudaSuccess) rc = fail(VORS_E_CUDA, "vors_gradient_norms_example", cudaGetErrorString(ce));
+    }
+    delete e;
+    return rc == VORS_OK ? levels : rc;
+}
+
 int vors_keyframe_create(const vors_config* cfg, const uint16_t* depth, const uint8_t* img, uint32_t rows, uint32_t cols,
                          int layout, vors_keyframe** out) {
     if (!out || !depth || !img) return fail(VORS_E_INVALID, "null argument");
@@ -886,7 +961,7 @@ int vors_keyframe_mask0(const vors_keyframe* kf, uint8_t* mask) {
     Engine* e = kf->e;
     CU_TRY(cudaSetDevice(e->device));
     const size_t I = size_t(e->rows) * e->cols;
-    if (e->cfg.candidate_mode == VORS_CANDIDATES_DENSE || e->g.L == 1) {
+    if (e->cfg.candidate_mode == VORS_CANDIDATES_DENSE || (e->g.L == 1 && e->cfg.candidate_mode != VORS_CANDIDATES_DSO)) {
         std::memset(mask, 1, I);
         return VORS_OK;
     }

@@ -152,6 +152,14 @@ void launch_h_total(Launcher& L, const Geom& g, const Intrinsics* intr, const ui
 void launch_jacobians(Launcher& L, const uint32_t* pts_level, int n, Intrinsics k, float* out6);
 void launch_se3_exp(Launcher& L, const float* xi6, Pose* out);
 
+// ---- implemented in dso_kernels.cu ------------------------------------------------------------------
+void launch_sqnorm_direct(Launcher& L, const uint8_t* img, int rows, int cols, int as_magnitude, uint16_t* out);
+void launch_bloc_sqnorm(Launcher& L, const uint8_t* fine, int rows_in, int rows, int cols, uint16_t* out);
+size_t dso_workspace_bytes(int rows, int cols);
+int dso_select_device(Launcher& L, const uint16_t* d_grad, int rows, int cols, int nb_target, int nb_iterations_left,
+                      unsigned long long seed, uint8_t* d_mask_out, uint8_t* ws, int* h_pinned_scratch, int* used_random,
+                      int* nb_candidates_out);
+
 // ---- implemented in align_kernel.cu ---------------------------------------------------------------
 struct AlignLaunchInfo {
     int block;

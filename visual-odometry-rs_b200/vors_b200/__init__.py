@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libvors_b200.so")
 MAX_LEVELS = 8
 COL_MAJOR, ROW_MAJOR = 0, 1
-CANDIDATES_COARSE_TO_FINE, CANDIDATES_DENSE = 0, 1
+CANDIDATES_COARSE_TO_FINE, CANDIDATES_DENSE, CANDIDATES_DSO = 0, 1, 2
 OK, OPTIMIZATION_FAILED, E_INVALID, E_CUDA, E_NOMEM = 0, 1, -1, -2, -3
 
 
@@ -111,6 +111,8 @@ SIGNATURES = {
     "vors_mean_pyramid": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
     "vors_gradients": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
     "vors_candidates_coarse_to_fine": (C.c_int, [C.c_uint16, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
+    "vors_candidates_dso": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, _vp, _P(C.c_int)]),
+    "vors_gradient_norms_example": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
     "vors_keyframe_create": (C.c_int, [_P(ConfigStruct), _vp, _vp, C.c_uint32, C.c_uint32, C.c_int, _P(_vp)]),
     "vors_keyframe_levels": (C.c_int, [_vp]),
     "vors_keyframe_n_points": (C.c_int, [_vp, C.c_uint32]),
@@ -369,6 +371,25 @@ def candidates_coarse_to_fine(diff_threshold, g2_levels):
     out = np.zeros(cat.size, np.uint8)
     _check(load_library().vors_candidates_coarse_to_fine(diff_threshold, _ptr(cat), rows, cols, len(g2_levels), _ptr(out)))
     return [m.astype(bool) for m in _split(out, shapes)]
+
+
+def candidates_dso(gradients, nb_target, nb_iterations_left=1, seed=0):
+    """`candidates::dso::select` (dso.rs:98-150) -> (mask [row, col] bool, nb block candidates, used_random_branch)."""
+    rows, cols = gradients.shape
+    out = np.zeros(rows * cols, np.uint8)
+    used = C.c_int()
+    nb = _count(load_library().vors_candidates_dso(_ptr(_cm(gradients, np.uint16)), rows, cols, nb_target, nb_iterations_left, seed,
+                                                   _ptr(out), C.byref(used)))
+    return _from_cm(out, rows, cols).astype(bool), nb, bool(used.value)
+
+
+def gradient_norms_example(img, max_levels):
+    """Example recipe: squared_norm_direct at level 0, bloc_squared_norm above; finest first."""
+    rows, cols = img.shape
+    shapes = pyramid_shapes(rows, cols, max_levels)
+    out = np.zeros(sum(r * c for r, c in shapes), np.uint16)
+    _count(load_library().vors_gradient_norms_example(_ptr(_cm(img, np.uint8)), rows, cols, max_levels, _ptr(out)))
+    return _split(out, shapes)
 
 
 def se3_exp(xi) -> Pose:
