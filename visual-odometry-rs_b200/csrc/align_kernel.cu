@@ -126,7 +126,8 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 __device__ __host__ constexpr int tri(int a, int b) { return a * 6 - a * (a - 1) / 2 + (b - a); }
 
 struct Acc {
-    float e, n;
+    float e;
+    int n;
     float g[6];
     float h[21];  // J J^T of the candidates that fell OUTSIDE (subtracted from H_total)
 };
@@ -174,7 +175,7 @@ struct Front {
 __device__ __forceinline__ void front(bool live, uint32_t pk, float rho, uint32_t gr, const float (&M)[12], const Intrinsics& k,
                                       const Pose* __restrict__ model, const uint8_t* __restrict__ img, int rows, int wm2i, int hm2i,
                                       float wm2, float hm2, Front& f) {
-    rho = live ? rho : 1.0f;  // padding lanes must stay finite (0 * NaN would poison the sums)
+    // padding lanes of a partial last chunk hold (pk, rho, grad) = 0 (k_compact_scan): finite, and J = 0 exactly
     const float x = u2f(pk & 0xFFFu), y = u2f((pk >> 12) & 0xFFFu);
     const float U = fmaf(M[0], x, fmaf(M[1], y, fmaf(M[3], rho, M[2])));
     const float V = fmaf(M[4], x, fmaf(M[5], y, fmaf(M[7], rho, M[6])));
@@ -192,11 +193,11 @@ __device__ __forceinline__ void front(bool live, uint32_t pk, float rho, uint32_
     // (float->int of NaN is 0, so NaN needs its own test; +-inf saturate and fail the range test).
     const int iu = __float2int_rd(u), iv = __float2int_rd(v);
     const bool inside = live && (unsigned(iu) < unsigned(wm2i)) && (unsigned(iv) < unsigned(hm2i)) && ((u + v) == (u + v));
-    const uint8_t* p = img + (inside ? iu * rows + iv : 0);
+    const uint8_t* p = img + (inside ? unsigned(iu * rows + iv) : 0u);  // unsigned offset: no sign extension
     f.t00 = __ldg(p);
     f.t10 = __ldg(p + 1);
-    f.t01 = __ldg(p + rows);
-    f.t11 = __ldg(p + rows + 1);
+    f.t01 = __ldg(p + unsigned(rows));
+    f.t11 = __ldg(p + unsigned(rows) + 1);
     f.a = u - u2f(uint32_t(iu) & 0xFFFu);
     f.b = v - u2f(uint32_t(iv) & 0xFFFu);
     f.pk = pk;
@@ -211,14 +212,15 @@ __device__ __forceinline__ void front(bool live, uint32_t pk, float rho, uint32_
 // back: Jacobian, bilinear sample, residual, accumulate.
 template <bool kSkew>
 __device__ __forceinline__ void back(const Front& f, const Intrinsics& k, Acc& acc) {
-    const float gu = f.live ? s16_2f(f.gr & 0xFFFFu) : 0.0f, gv = f.live ? s16_2f(f.gr >> 16) : 0.0f;
+    const float gu = s16_2f(f.gr & 0xFFFFu), gv = s16_2f(f.gr >> 16);
     float J[6];
     jacobian_at<kSkew>(gu, gv, f.x, f.y, f.rho, k, J);
     const float a = f.a, b = f.b;
+    // bilinear blend exactly as lm_optimizer.rs:241-246 writes it (a along x, b along y)
     const float val = (1.0f - b) * (1.0f - a) * u2f(f.t00) + b * (1.0f - a) * u2f(f.t10) + (1.0f - b) * a * u2f(f.t01) + b * a * u2f(f.t11);
     const float r = f.inside ? val - u2f(f.pk >> 24) : 0.0f;
     acc.e = fmaf(r, r, acc.e);
-    acc.n += f.inside ? 1.0f : 0.0f;
+    acc.n += f.inside ? 1 : 0;
 #pragma unroll
     for (int c = 0; c < 6; ++c) acc.g[c] = fmaf(J[c], r, acc.g[c]);
     // H = H_total - sum over outside candidates of J J^T: only warps that own an outside candidate pay for it
@@ -389,7 +391,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_align(const AlignParams P) {
                     for (int c = 0; c < 12; ++c) M[c] = S.M[c];
                     Acc acc;
                     acc.e = 0.0f;
-                    acc.n = 0.0f;
+                    acc.n = 0;
 #pragma unroll
                     for (int c = 0; c < 6; ++c) acc.g[c] = 0.0f;
 #pragma unroll
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_align(const AlignParams P) {
                     }
                     back<kSkew>(fy, k, acc);
                     vals[0] = acc.e;
-                    vals[1] = acc.n;
+                    vals[1] = float(acc.n);
 #pragma unroll
                     for (int c = 0; c < 6; ++c) vals[2 + c] = acc.g[c];
 #pragma unroll

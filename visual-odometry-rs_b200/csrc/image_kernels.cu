@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kCompactBlock) k_compact_count(const Geom g, c
 
 // One CTA per (level, stream): exclusive scan of that level's block counts (in place) + total.
 __global__ void __launch_bounds__(1024) k_compact_scan(const Geom g, int* __restrict__ blk_count, int* __restrict__ n_points,
-                                                       const int* __restrict__ items) {
+                                                       uint32_t* __restrict__ pts_slab, const int* __restrict__ items) {
     __shared__ int warp_sum[32];
     __shared__ int carry;
     const int it = item_of(items, blockIdx.y);
@@ -264,6 +264,12 @@ __global__ void __launch_bounds__(1024) k_compact_scan(const Geom g, int* __rest
         __syncthreads();
     }
     if (threadIdx.x == 0) n_points[it * kMaxLevels + l] = carry;
+    // zero the padding of the last (partial) chunk: the align kernel stages whole chunks and relies on padding
+    // candidates being (pk, idepth, grad) = 0 -> finite arithmetic and exactly zero contributions
+    const int total = carry, padded = (total + kChunk - 1) / kChunk * kChunk;
+    uint32_t* lvl = pts_slab + 3 * (size_t(it) * g.pt_total + g.pt_off[l]);
+    for (int i = total + threadIdx.x; i < padded; i += blockDim.x)
+        for (int f = 0; f < 3; ++f) lvl[pt_word(i, f)] = 0u;
 }
 
 __global__ void __launch_bounds__(kCompactBlock) k_compact_scatter(const Geom g, const float* __restrict__ idepth_slab,
@@ -440,7 +446,7 @@ void launch_compact(Launcher& L, const Geom& g, const float* idepth_slab, const 
     dim3 gridb(g.blk_total, m);
     k_compact_count<<<gridb, kCompactBlock, 0, L.stream>>>(g, idepth_slab, blk_count, items);
     dim3 grids(g.L, m);
-    k_compact_scan<<<grids, 1024, 0, L.stream>>>(g, blk_count, n_points, items);
+    k_compact_scan<<<grids, 1024, 0, L.stream>>>(g, blk_count, n_points, pts_slab, items);
     k_compact_scatter<<<gridb, kCompactBlock, 0, L.stream>>>(g, idepth_slab, pyr_slab, grad_slab, blk_count, pts_slab, items);
     L.launches += 3;
 }
