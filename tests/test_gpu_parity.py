@@ -486,3 +486,24 @@ def test_keyframe_dso_mask_matches_oracle(vb, oracle):
     for l in range(5):
         assert kf.n_points(l) == okf.n_points(l)
         assert np.array_equal(kf.points(l)[0], okf.points(l)[0])
+
+
+def test_large_batch_overlapped_upload_path(vb, oracle):
+    """n >= 64 host-buffer batches are processed as two half batches (H2D of the second overlaps the first's alignment,
+    each alignment spread over several CTAs): results must still match per-stream oracle trackers."""
+    n = 67  # odd: halves of 33 and 34 streams
+    seqs = [synth.make_sequence(seed=700 + i, n_frames=3, rows=60, cols=80, step_v=0.01, step_w=0.006) for i in range(n)]
+    cfg, ocfg = _cfgs(vb, oracle, seqs[0][0], nb_levels=3)
+    stack = lambda k: (np.stack([s[1][k][0] for s in seqs]), np.stack([s[1][k][1] for s in seqs]))
+    g, d = stack(0)
+    bt = vb.BatchTracker(cfg, np.zeros(n), d, np.zeros(n), g)
+    for k in (1, 2):
+        g, d = stack(k)
+        status, stats = bt.track(np.full(n, float(k)), d, np.full(n, float(k)), g)
+        assert not status.any()
+    _, poses = bt.current_frames()
+    for i in range(n):
+        ot = oracle.Tracker(ocfg, 0.0, seqs[i][1][0][1], 0.0, seqs[i][1][0][0])
+        for k in (1, 2):
+            ot.track(float(k), seqs[i][1][k][1], float(k), seqs[i][1][k][0])
+        _pose_close(poses[i], ot.current_frame()[1].as_array(), oracle)

@@ -75,6 +75,8 @@ class Engine {
     Geom g{};
     Intrinsics intr[kMaxLevels]{};
     Launcher L{};
+    Launcher LC{};                   // copy stream: H2D + transposes of the next chunk overlap the align kernel
+    cudaEvent_t ev_up[2]{};
     AlignLaunchInfo info{};
     std::vector<StreamState> st;
     bool tracing = false;
@@ -133,6 +135,10 @@ class Engine {
             if (p) cudaFreeHost(p);
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
+        for (auto& e : ev_up)
+            if (e) cudaEventDestroy(e);
+        if (LC.stream) cudaStreamDestroy(LC.stream);
+        LC.stream = nullptr;
         if (L.stream) cudaStreamDestroy(L.stream);
         L.stream = nullptr;
         d_pyr = nullptr;
@@ -191,7 +197,9 @@ class Engine {
         g.blk_total = boff;
 
         CU_TRY(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+        CU_TRY(cudaStreamCreateWithFlags(&LC.stream, cudaStreamNonBlocking));
         for (auto& e : ev) CU_TRY(cudaEventCreate(&e));
+        for (auto& e : ev_up) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CU_TRY(align_query(&info));
         if (info.max_resident_ctas < 1) return fail(VORS_E_CUDA, "align kernel cannot be resident on this device");
 
@@ -261,29 +269,32 @@ class Engine {
     }
 
     // ---- uploads ------------------------------------------------------------------------------
-    // Frames of all n streams into level 0 of the frame pyramid (column-major).
-    int upload_images_host(const uint8_t* const* img) {
+    // Frames of streams [start, start + m) into level 0 of their frame pyramids (column-major), on launcher X's stream.
+    int upload_images_host_range(const uint8_t* const* img, int start, int m, Launcher& X) {
         const size_t I = size_t(rows) * cols;
         bool contiguous = true;
-        for (int i = 1; i < n && contiguous; ++i) contiguous = (img[i] == img[0] + size_t(i) * I);
+        for (int i = 1; i < m && contiguous; ++i) contiguous = (img[start + i] == img[start] + size_t(i) * I);
+        uint8_t* pyr0 = d_pyr + size_t(start) * g.pix_total;
         if (layout == VORS_COL_MAJOR) {
             if (contiguous) {
-                CU_TRY(cudaMemcpy2DAsync(d_pyr, size_t(g.pix_total), img[0], I, I, size_t(n), cudaMemcpyHostToDevice, L.stream));
+                CU_TRY(cudaMemcpy2DAsync(pyr0, size_t(g.pix_total), img[start], I, I, size_t(m), cudaMemcpyHostToDevice, X.stream));
             } else {
-                for (int i = 0; i < n; ++i)
-                    CU_TRY(cudaMemcpyAsync(d_pyr + size_t(i) * g.pix_total, img[i], I, cudaMemcpyHostToDevice, L.stream));
+                for (int i = 0; i < m; ++i)
+                    CU_TRY(cudaMemcpyAsync(pyr0 + size_t(i) * g.pix_total, img[start + i], I, cudaMemcpyHostToDevice, X.stream));
             }
         } else {
+            uint8_t* stage = d_stage8 + size_t(start) * I;
             if (contiguous) {
-                CU_TRY(cudaMemcpyAsync(d_stage8, img[0], I * size_t(n), cudaMemcpyHostToDevice, L.stream));
+                CU_TRY(cudaMemcpyAsync(stage, img[start], I * size_t(m), cudaMemcpyHostToDevice, X.stream));
             } else {
-                for (int i = 0; i < n; ++i)
-                    CU_TRY(cudaMemcpyAsync(d_stage8 + size_t(i) * I, img[i], I, cudaMemcpyHostToDevice, L.stream));
+                for (int i = 0; i < m; ++i)
+                    CU_TRY(cudaMemcpyAsync(stage + size_t(i) * I, img[start + i], I, cudaMemcpyHostToDevice, X.stream));
             }
-            launch_transpose_u8(L, d_stage8, d_pyr, size_t(g.pix_total), nullptr, n, rows, cols);
+            launch_transpose_u8(X, stage, pyr0, size_t(g.pix_total), nullptr, m, rows, cols);
         }
         return VORS_OK;
     }
+    int upload_images_host(const uint8_t* const* img) { return upload_images_host_range(img, 0, n, L); }
 
     int upload_images_device(const uint8_t* img_dev) {  // column-major, n*rows*cols contiguous
         const size_t I = size_t(rows) * cols;
@@ -377,12 +388,12 @@ class Engine {
         return VORS_OK;
     }
 
-    AlignParams make_params(int n_jobs, int team) const {
+    AlignParams make_params(int n_jobs, int team, int start = 0) const {
         AlignParams p{};
-        p.jobs = d_jobs;
-        p.init = d_init;
-        p.results = d_results;
-        p.trace = tracing ? d_trace : nullptr;
+        p.jobs = d_jobs + start;
+        p.init = d_init + start;
+        p.results = d_results + start;
+        p.trace = tracing ? d_trace + size_t(start) * kTraceCap : nullptr;
         p.scratch = d_scratch;
         p.n_jobs = n_jobs;
         p.team = team;
@@ -412,13 +423,13 @@ class Engine {
         *n_teams = std::max(1, std::min(n_jobs, cap / t));
     }
 
-    int run_align(int n_jobs, int max_points) {
+    int run_align(int n_jobs, int max_points, int start = 0) {
         int team, n_teams;
         choose_team(n_jobs, max_points, &team, &n_teams);
         int rc;
         if ((rc = ensure_trace()) != VORS_OK) return rc;
         if (team > 1) CU_TRY(cudaMemsetAsync(d_scratch, 0, size_t(n_teams) * sizeof(TeamScratch), L.stream));
-        const AlignParams p = make_params(n_jobs, team);
+        const AlignParams p = make_params(n_jobs, team, start);
         CU_TRY(launch_align(L, p, n_teams));
         return VORS_OK;
     }
@@ -427,26 +438,50 @@ class Engine {
     int track(const double* depth_ts, const uint16_t* const* depth, const uint16_t* depth_dev, const double* img_ts,
               const uint8_t* const* img, const uint8_t* img_dev, int* status, vors_track_stats* stats) {
         CU_TRY(cudaSetDevice(device));
-        const unsigned long long launches0 = L.launches;
+        const unsigned long long launches0 = L.launches + LC.launches;
         int rc;
         CU_TRY(cudaEventRecord(ev[0], L.stream));
         // :177 lm_model = current_frame_pose^-1 * keyframe_pose
         for (int i = 0; i < n; ++i) h_init[i] = pose_mul(pose_inverse(st[size_t(i)].cur_pose), st[size_t(i)].kf_pose);
         CU_TRY(cudaMemcpyAsync(d_init, h_init, size_t(n) * sizeof(Pose), cudaMemcpyHostToDevice, L.stream));
+        int max_points = 0;
+        for (int i = 0; i < n; ++i) max_points = std::max(max_points, h_n_points[i * kMaxLevels]);
+        // Host frames of a large batch are processed as two half batches: the H2D copy (+ transpose) of the second half
+        // runs on the copy stream while the first half is being aligned (each half still fills the device: the align
+        // kernel spreads every alignment over cap / (n/2) CTAs).  SURVEY §8f rank 2.
+        const int n_chunks = (!img_dev && n >= 64 && cfg.team_size == 0) ? 2 : 1;
         if (img_dev) {
             if ((rc = upload_images_device(img_dev)) != VORS_OK) return rc;
         } else {
             if (!img) return fail(VORS_E_INVALID, "null image pointer array");
             for (int i = 0; i < n; ++i)
                 if (!img[i]) return fail(VORS_E_INVALID, "null image pointer");
-            if ((rc = upload_images_host(img)) != VORS_OK) return rc;
+            if (n_chunks == 1) {
+                if ((rc = upload_images_host(img)) != VORS_OK) return rc;
+            } else {
+                CU_TRY(cudaEventRecord(ev_up[0], L.stream));       // the copy stream must not overtake earlier work on L
+                CU_TRY(cudaStreamWaitEvent(LC.stream, ev_up[0], 0));
+                for (int c = 0; c < n_chunks; ++c) {
+                    const int start = c * (n / 2), m = c == 0 ? n / 2 : n - n / 2;
+                    if ((rc = upload_images_host_range(img, start, m, LC)) != VORS_OK) return rc;
+                    CU_TRY(cudaEventRecord(ev_up[c], LC.stream));
+                }
+            }
         }
         CU_TRY(cudaEventRecord(ev[1], L.stream));
-        launch_pyramid(L, g, d_pyr, nullptr, n);  // :178
-        CU_TRY(cudaEventRecord(ev[2], L.stream));
-        int max_points = 0;
-        for (int i = 0; i < n; ++i) max_points = std::max(max_points, h_n_points[i * kMaxLevels]);
-        if ((rc = run_align(n, max_points)) != VORS_OK) return rc;  // :181-201
+        if (n_chunks == 1) {
+            launch_pyramid(L, g, d_pyr, nullptr, n);  // :178
+            CU_TRY(cudaEventRecord(ev[2], L.stream));
+            if ((rc = run_align(n, max_points)) != VORS_OK) return rc;  // :181-201
+        } else {
+            CU_TRY(cudaEventRecord(ev[2], L.stream));
+            for (int c = 0; c < n_chunks; ++c) {
+                const int start = c * (n / 2), m = c == 0 ? n / 2 : n - n / 2;
+                CU_TRY(cudaStreamWaitEvent(L.stream, ev_up[c], 0));
+                launch_pyramid(L, g, d_pyr + size_t(start) * g.pix_total, nullptr, m);
+                if ((rc = run_align(m, max_points, start)) != VORS_OK) return rc;
+            }
+        }
         CU_TRY(cudaEventRecord(ev[3], L.stream));
         CU_TRY(cudaMemcpyAsync(h_results, d_results, size_t(n) * sizeof(AlignResult), cudaMemcpyDeviceToHost, L.stream));
         CU_TRY(cudaStreamSynchronize(L.stream));
@@ -500,7 +535,7 @@ class Engine {
         CU_TRY(cudaEventRecord(ev[4], L.stream));
         CU_TRY(cudaStreamSynchronize(L.stream));
         for (int k = 0; k < 4; ++k) CU_TRY(cudaEventElapsedTime(&last_ms[k], ev[k], ev[k + 1]));
-        last_launches = L.launches - launches0;
+        last_launches = (L.launches + LC.launches) - launches0;
         return any_failed ? VORS_OPTIMIZATION_FAILED : VORS_OK;
     }
 
@@ -1086,6 +1121,8 @@ int vors_se3_exp(const float xi[6], vors_pose* out) {
     float* d = nullptr;
     CU_TRY(cudaMalloc(&d, 6 * sizeof(float) + sizeof(Pose)));
     Launcher L{};
+    Launcher LC{};                   // copy stream: H2D + transposes of the next chunk overlap the align kernel
+    cudaEvent_t ev_up[2]{};
     L.stream = nullptr;
     cudaError_t ce = cudaMemcpy(d, xi, 6 * sizeof(float), cudaMemcpyHostToDevice);
     Pose p{};
