@@ -128,7 +128,10 @@ def _cmp_pass(got, ref64, ref32):
     e32, n32, g32, H32 = ref32
     assert n == n64 == n32
     assert abs(e - e64) <= 1e-5 * abs(e64) + 1e-7
-    assert np.all(np.abs(g - g64) <= 1e-5 * np.abs(g64).max() + 1e-3)
+    # g = sum J r is first-order sensitive to the warped coordinates: the folded-matrix warp and the reference's
+    # operation order differ by a few 1e-6 px (sub-ulp, but not zero-mean over a regular grid), which the image
+    # gradient turns into ~2e-5 of |g|max (measured 1.6e-5 with skew != 0, 7e-6 without); E and H are second-order.
+    assert np.all(np.abs(g - g64) <= 5e-5 * np.abs(g64).max() + 1e-3)
     assert np.all(np.abs(H - H64) <= 1e-5 * np.abs(H64).max())
     assert abs(e - e32) <= 2e-4 * abs(e32) + 1e-7
     assert np.all(np.abs(g - g32) <= 2e-4 * np.abs(g32).max() + 1e-2)
@@ -507,3 +510,49 @@ def test_large_batch_overlapped_upload_path(vb, oracle):
         for k in (1, 2):
             ot.track(float(k), seqs[i][1][k][1], float(k), seqs[i][1][k][0])
         _pose_close(poses[i], ot.current_frame()[1].as_array(), oracle)
+
+
+# ---- intrinsics variants: skew != 0 (general Jacobian kernel), negative fy (ICL-NUIM), full HD -------------------
+
+def _synth_pair_with_intrinsics(seed, rows, cols, **intr):
+    """Frames rendered with the fr1-style pinhole; the tracker is then GIVEN other intrinsics.  Parity only needs both
+    sides to consume identical inputs and parameters, not a physically consistent camera."""
+    scene, f0, f1, _ = synth.make_pair(seed=seed, rows=rows, cols=cols, max_v=0.02, max_w=0.01)
+    kw = synth.scene_config_kwargs(scene)
+    kw.update(intr)
+    return f0, f1, kw
+
+
+@pytest.mark.parametrize("intr", [dict(skew=0.7), dict(skew=-1.3, fx=300.0), dict(fy=-480.0, fx=481.2, cx=159.5, cy=119.5)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_skew_and_negative_focal_variants(vb, oracle, intr, mode):
+    f0, f1, kw = _synth_pair_with_intrinsics(81, 240, 320, **intr)
+    kw.update(nb_levels=4, candidate_mode=mode)
+    cfg, ocfg = vb.Config(**kw), oracle.default_config(**kw)
+    kf = vb.Keyframe(cfg, f0[1], f0[0])
+    okf = oracle.Keyframe(ocfg, f0[1], f0[0])
+    pyr1 = oracle.mean_pyramid(f1[0], 4)
+    for l in (3, 0):
+        jac, ojac = kf.jacobians(l), okf.points(l)[2]
+        assert np.all(np.abs(jac - ojac) <= 2e-6 * (np.abs(ojac).max(0) + 1e-30) + 1e-6 * np.abs(ojac))
+        m = oracle.se3_exp([0.004, -0.002, 0.003, 0.001, 0.002, -0.001])
+        _cmp_pass(kf.align_pass(l, pyr1[l], vb.Pose.from_arrays(m.t, m.q)), okf.eval(l, pyr1[l], m, 1), okf.eval(l, pyr1[l], m, 0))
+    t = cfg.init(0.0, f0[1], 0.0, f0[0])
+    t.set_tracing(True)
+    stats = t.track(1.0, f1[1], 1.0, f1[0])
+    ot = oracle.Tracker(ocfg, 0.0, f0[1], 0.0, f0[0])
+    ost, ostats, otrace = ot.track(1.0, f1[1], 1.0, f1[0], trace_cap=512)
+    assert stats.status == ostats.status
+    _same_trace(t.last_trace(), otrace, DENSE_E_TOL if mode else 2e-4)
+    _pose_close(t.current_frame()[1].as_array(), ot.current_frame()[1].as_array(), oracle)
+
+
+def test_full_hd_coarse_to_fine_config5_shape(vb, oracle):
+    """BASELINE config 5 shape: 1920x1080, coarse-to-fine ("semi-dense") candidates, 6 levels, adaptive LM."""
+    scene, frames, poses = synth.make_sequence(seed=5000, n_frames=3, rows=1080, cols=1920)
+    t, ot, out = _run_both(vb, oracle, scene, frames, nb_levels=6)
+    for k, (stats, trace, (ts, pose), ostats, otrace, (ots, opose)) in enumerate(out, 1):
+        assert stats.status == ostats.status == 0
+        assert list(stats.n_points)[:6] == list(ostats.n_points)[:6]
+        _same_trace(trace, otrace)
+        _pose_close(pose.as_array(), opose.as_array(), oracle)

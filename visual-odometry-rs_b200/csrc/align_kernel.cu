@@ -110,10 +110,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // 2-ALU-op magic-number conversion is only used where it fuses with work that is needed anyway).
 __device__ __forceinline__ float u2f(uint32_t v) { return float(v); }
 __device__ __forceinline__ float s16_2f(uint32_t v16) { return float(int(short(v16))); }
+// 1/x: MUFU.RCP seed + one Newton step (2 FMAs) = correctly rounded to within 1 ulp without the slow-path range
+// checks of an IEEE division; x = 0 / inf / NaN give inf / NaN, which the inside test rejects like the reference.
 __device__ __forceinline__ float rcp_approx(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
 }
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
