@@ -407,16 +407,17 @@ class Engine {
         return p;
     }
 
-    // CTAs per alignment: 1 when the batch alone fills the device, otherwise spread each alignment over
-    // enough CTAs for ~4 level-0 candidates per thread, bounded by what can be co-resident.
+    // CTAs per alignment: 1 when the batch alone fills the device, otherwise spread each alignment over enough CTAs for
+    // ~16 level-0 candidates per thread (measured: per-pass barrier + partial-sum cost grows with the team, so sparse
+    // coarse-to-fine keyframes want 1-5 CTAs and a dense 640x480 keyframe ~64), bounded by what can be co-resident.
     void choose_team(int n_jobs, int max_points, int* team, int* n_teams) const {
         const int cap = info.max_resident_ctas;
         int t = 1;
         if (cfg.team_size) {
             t = int(cfg.team_size);
         } else if (n_jobs < cap) {
-            const int by_points = (max_points + info.block * 4 - 1) / (info.block * 4);
-            t = std::max(1, std::min(cap / n_jobs, by_points));
+            const int by_points = (max_points + info.block * 16 - 1) / (info.block * 16);
+            t = std::max(1, std::min(std::min(cap / n_jobs, by_points), 64));
         }
         t = std::max(1, std::min(t, std::min(kMaxTeam, cap)));
         *team = t;
