@@ -246,6 +246,11 @@ int vors_align(const vors_keyframe* kf, const uint8_t* img, int layout, const vo
 
 /* `se3::exp` (src/math/se3.rs:65-95) evaluated by the device code the LM step uses. */
 int vors_se3_exp(const float xi[6], vors_pose* out);
+/* `se3::log` (src/math/se3.rs:99-130), `so3::exp` / `so3::log` (src/math/so3.rs:61-99; quaternion as x y z w): utilities for
+ * trajectory error metrics, evaluated on the device in f32 like the reference.  Not on the tracking path. */
+int vors_se3_log(const vors_pose* pose, float xi[6]);
+int vors_so3_exp(const float w[3], float q[4]);
+int vors_so3_log(const float q[4], float w[3]);
 
 #ifdef __cplusplus
 }

@@ -556,3 +556,29 @@ def test_full_hd_coarse_to_fine_config5_shape(vb, oracle):
         assert list(stats.n_points)[:6] == list(ostats.n_points)[:6]
         _same_trace(trace, otrace)
         _pose_close(pose.as_array(), opose.as_array(), oracle)
+
+
+# ---- se3::log / so3 utilities on the device -------------------------------------------------
+
+def test_lie_utilities_match_oracle_and_round_trip(vb, oracle):
+    rng = np.random.default_rng(12)
+    for i in range(30):
+        # the reference's generators: rotations from Euler angles (so3.rs:146, se3.rs:177)
+        q = np.zeros(4, np.float32)
+        oracle.lib().ref_quat_from_euler(*rng.uniform(-3, 3, 3).astype(np.float32), q)
+        t = rng.uniform(-5, 5, 3).astype(np.float32)
+        pose = oracle.Pose.from_arrays(t, q)
+        xi_ref = oracle.se3_log(pose)
+        xi = vb.se3_log(vb.Pose.from_arrays(t, q))
+        assert np.allclose(xi, xi_ref, rtol=1e-4, atol=1e-5)
+        w_ref = np.zeros(3, np.float32)
+        oracle.lib().ref_so3_log(q, w_ref)
+        assert np.allclose(vb.so3_log(q), w_ref, rtol=1e-5, atol=1e-6)
+        q_ref = np.zeros(4, np.float32)
+        oracle.lib().ref_so3_exp(w_ref, q_ref)
+        assert np.allclose(vb.so3_exp(w_ref), q_ref, atol=1e-6)
+        # log_exp_round_trip (se3.rs:159-173, epsilon 1e-4) on the device
+        back = vb.se3_exp(xi).as_array()
+        a = pose.as_array()
+        assert np.allclose(back, a, atol=2e-4) or np.allclose(back, np.concatenate([a[:3], -a[3:]]), atol=2e-4)
+    assert np.array_equal(vb.se3_log(vb.Pose.identity()), np.zeros(6, np.float32))  # exp_log_round_trip on zero (se3.rs:145-148)

@@ -36,6 +36,27 @@ static int fail(int code, const char* what, const char* detail = nullptr) {
         }                                                                            \
     } while (0)
 
+// Makes `dev` current for the enclosing scope and restores the caller's device afterwards (the library must not
+// change the calling thread's current device as a side effect).
+struct DeviceScope {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceScope(int dev) {
+        int cur = -1;
+        err = cudaGetDevice(&cur);
+        if (err == cudaSuccess && cur != dev) {
+            err = cudaSetDevice(dev);
+            if (err == cudaSuccess) prev = cur;
+        }
+    }
+    ~DeviceScope() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define DEVICE_SCOPE(dev)          \
+    DeviceScope _device_scope(dev); \
+    CU_TRY(_device_scope.err)
+
 static Pose to_pose(const vors_pose& p) { return Pose{{p.t[0], p.t[1], p.t[2]}, {p.q[0], p.q[1], p.q[2], p.q[3]}}; }
 static vors_pose from_pose(const Pose& p) {
     vors_pose o;
@@ -122,10 +143,8 @@ class Engine {
     ~Engine() { destroy(); }
 
     void destroy() {
-        if (L.stream) {
-            cudaSetDevice(device);
-            cudaStreamSynchronize(L.stream);
-        }
+        DeviceScope scope(device);
+        if (L.stream) cudaStreamSynchronize(L.stream);
         void* dev_ptrs[] = {d_pyr, d_stage8, d_stage16, d_depth, d_grad, d_g2, d_mask, d_idepth, d_weight, d_pts,
                             d_blk_count, d_n_points, d_h_total, d_items, d_jobs, d_init, d_results, d_scratch, d_trace, d_tmp, d_gradmag, d_dso_ws};
         for (void* p : dev_ptrs)
@@ -171,7 +190,7 @@ class Engine {
         } else {
             CU_TRY(cudaGetDevice(&device));
         }
-        CU_TRY(cudaSetDevice(device));
+        DEVICE_SCOPE(device);
         cudaDeviceProp prop;
         CU_TRY(cudaGetDeviceProperties(&prop, device));
         if (prop.major != 10) return fail(VORS_E_CUDA, "libvors_b200 is built for sm_100a only; device is not compute capability 10.x");
@@ -355,7 +374,7 @@ class Engine {
     // n x Config::init (inverse_compositional.rs:74-100)
     int init_keyframes(const double* depth_ts, const uint16_t* const* depth, const uint16_t* depth_dev, const double* img_ts,
                        const uint8_t* const* img, const uint8_t* img_dev) {
-        CU_TRY(cudaSetDevice(device));
+        DEVICE_SCOPE(device);
         int rc;
         if (img_dev) {
             if ((rc = upload_images_device(img_dev)) != VORS_OK) return rc;
@@ -438,7 +457,7 @@ class Engine {
     // n x Tracker::track (inverse_compositional.rs:170-240)
     int track(const double* depth_ts, const uint16_t* const* depth, const uint16_t* depth_dev, const double* img_ts,
               const uint8_t* const* img, const uint8_t* img_dev, int* status, vors_track_stats* stats) {
-        CU_TRY(cudaSetDevice(device));
+        DEVICE_SCOPE(device);
         const unsigned long long launches0 = L.launches + LC.launches;
         int rc;
         CU_TRY(cudaEventRecord(ev[0], L.stream));
@@ -557,7 +576,7 @@ class Engine {
         const int have = h_results[stream].trace_len;
         const int k = std::max(0, std::min(have, cap));
         if (k > 0 && out) {
-            CU_TRY(cudaSetDevice(device));
+            DEVICE_SCOPE(device);
             CU_TRY(cudaMemcpy(out, d_trace + size_t(stream) * kTraceCap, size_t(k) * sizeof(vors_trace_rec), cudaMemcpyDeviceToHost));
         }
         if (len) *len = k;
@@ -954,7 +973,7 @@ int vors_keyframe_points(const vors_keyframe* kf, uint32_t level, uint32_t* xy, 
     Engine* e = kf->e;
     const int np = e->h_n_points[level];
     if (np == 0) return VORS_OK;
-    CU_TRY(cudaSetDevice(e->device));
+    DEVICE_SCOPE(e->device);
     const size_t cnt = size_t(np);
     const size_t words = (cnt + kChunk - 1) / kChunk * (3 * kChunk);
     std::vector<uint32_t> blk(words), pk(cnt), gr(cnt);
@@ -983,7 +1002,7 @@ int vors_keyframe_jacobians(const vors_keyframe* kf, uint32_t level, float* jac6
     Engine* e = kf->e;
     const int np = e->h_n_points[level];
     if (np == 0) return VORS_OK;
-    CU_TRY(cudaSetDevice(e->device));
+    DEVICE_SCOPE(e->device);
     int rc = e->need_tmp(size_t(np) * 24);
     if (rc != VORS_OK) return rc;
     launch_jacobians(e->L, e->d_pts + 3 * size_t(e->g.pt_off[level]), np, e->intr[level], e->d_tmp);
@@ -995,7 +1014,7 @@ int vors_keyframe_jacobians(const vors_keyframe* kf, uint32_t level, float* jac6
 int vors_keyframe_mask0(const vors_keyframe* kf, uint8_t* mask) {
     if (!kf || !mask) return fail(VORS_E_INVALID, "null argument");
     Engine* e = kf->e;
-    CU_TRY(cudaSetDevice(e->device));
+    DEVICE_SCOPE(e->device);
     const size_t I = size_t(e->rows) * e->cols;
     if (e->cfg.candidate_mode == VORS_CANDIDATES_DENSE || (e->g.L == 1 && e->cfg.candidate_mode != VORS_CANDIDATES_DSO)) {
         std::memset(mask, 1, I);
@@ -1008,7 +1027,7 @@ int vors_keyframe_mask0(const vors_keyframe* kf, uint8_t* mask) {
 int vors_keyframe_idepth_map(const vors_keyframe* kf, uint32_t level, float* idepth) {
     if (!kf || !idepth || level >= uint32_t(kf->e->g.L)) return fail(VORS_E_INVALID, "bad argument");
     Engine* e = kf->e;
-    CU_TRY(cudaSetDevice(e->device));
+    DEVICE_SCOPE(e->device);
     CU_TRY(cudaMemcpy(idepth, e->d_idepth + e->g.off[level], size_t(e->g.rows[level]) * e->g.cols[level] * 4,
                       cudaMemcpyDeviceToHost));
     return VORS_OK;
@@ -1023,7 +1042,7 @@ void vors_keyframe_destroy(vors_keyframe* kf) {
 // Run one ad-hoc job on a keyframe engine (stream 0) and read the result back.
 static int run_single_job(Engine* e, int lvl_first, int lvl_last, int flow_level, int pass_only, const vors_pose* init,
                           bool want_trace) {
-    CU_TRY(cudaSetDevice(e->device));
+    DEVICE_SCOPE(e->device);
     e->fill_job(e->h_jobs[0], 0, lvl_first, lvl_last, flow_level, pass_only);
     e->h_init[0] = to_pose(*init);
     CU_TRY(cudaMemcpyAsync(e->d_jobs, e->h_jobs, sizeof(AlignJob), cudaMemcpyHostToDevice, e->L.stream));
@@ -1049,7 +1068,7 @@ int vors_align_pass(const vors_keyframe* kf, uint32_t level, const uint8_t* imag
                     int32_t* n_inside, float g[6], float H[36]) {
     if (!kf || !image || !model || level >= uint32_t(kf->e->g.L)) return fail(VORS_E_INVALID, "bad argument");
     Engine* e = kf->e;
-    CU_TRY(cudaSetDevice(e->device));
+    DEVICE_SCOPE(e->device);
     const size_t cnt = size_t(e->g.rows[level]) * e->g.cols[level];
     CU_TRY(cudaMemcpyAsync(e->d_pyr + e->g.off[level], image, cnt, cudaMemcpyHostToDevice, e->L.stream));
     int rc = run_single_job(e, int(level), int(level), -1, 1, model, false);
@@ -1071,7 +1090,7 @@ int vors_align_level(const vors_keyframe* kf, uint32_t level, const uint8_t* ima
                      int32_t* n_iter, float* energy, vors_trace_rec* trace, int trace_cap, int* trace_len) {
     if (!kf || !image || !init || level >= uint32_t(kf->e->g.L)) return fail(VORS_E_INVALID, "bad argument");
     Engine* e = kf->e;
-    CU_TRY(cudaSetDevice(e->device));
+    DEVICE_SCOPE(e->device);
     const size_t cnt = size_t(e->g.rows[level]) * e->g.cols[level];
     CU_TRY(cudaMemcpyAsync(e->d_pyr + e->g.off[level], image, cnt, cudaMemcpyHostToDevice, e->L.stream));
     int rc = run_single_job(e, int(level), int(level), -1, 0, init, trace != nullptr);
@@ -1088,7 +1107,7 @@ int vors_align(const vors_keyframe* kf, const uint8_t* img, int layout, const vo
                vors_track_stats* stats, vors_trace_rec* trace, int trace_cap, int* trace_len) {
     if (!kf || !img || !init) return fail(VORS_E_INVALID, "bad argument");
     Engine* e = kf->e;
-    CU_TRY(cudaSetDevice(e->device));
+    DEVICE_SCOPE(e->device);
     const int keep_layout = e->layout;
     e->layout = layout;
     const uint8_t* one[1] = {img};
@@ -1115,6 +1134,31 @@ int vors_align(const vors_keyframe* kf, const uint8_t* img, int layout, const vo
     if (trace && (rc = fetch_trace(e, trace, trace_cap, trace_len)) != VORS_OK) return rc;
     return r.status;
 }
+
+// se3::log / so3::exp / so3::log (src/math/se3.rs:99-130, so3.rs:61-99) on the device: utilities for trajectory error
+// metrics, not on the tracking path.
+static int run_lie(int op, const float* in, int n_in, float* out, int n_out) {
+    if (!in || !out) return fail(VORS_E_INVALID, "null argument");
+    if (vors_device_count() == 0) return fail(VORS_E_CUDA, "no CUDA device available (libvors_b200 has no CPU fallback)");
+    float* d = nullptr;
+    CU_TRY(cudaMalloc(&d, 16 * sizeof(float)));
+    Launcher L{};
+    cudaError_t ce = cudaMemcpy(d, in, size_t(n_in) * sizeof(float), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) {
+        launch_lie(L, op, d, d + 8);
+        ce = cudaMemcpy(out, d + 8, size_t(n_out) * sizeof(float), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d);
+    if (ce != cudaSuccess) return fail(VORS_E_CUDA, "lie-group utility", cudaGetErrorString(ce));
+    return VORS_OK;
+}
+int vors_se3_log(const vors_pose* pose, float xi[6]) {
+    if (!pose) return fail(VORS_E_INVALID, "null argument");
+    const float in[7] = {pose->t[0], pose->t[1], pose->t[2], pose->q[0], pose->q[1], pose->q[2], pose->q[3]};
+    return run_lie(1, in, 7, xi, 6);
+}
+int vors_so3_exp(const float w[3], float q[4]) { return run_lie(2, w, 3, q, 4); }
+int vors_so3_log(const float q[4], float w[3]) { return run_lie(3, q, 4, w, 3); }
 
 int vors_se3_exp(const float xi[6], vors_pose* out) {
     if (!xi || !out) return fail(VORS_E_INVALID, "null argument");

@@ -384,6 +384,22 @@ __global__ void k_se3_exp(const float* __restrict__ xi6, Pose* __restrict__ out)
     *out = se3_exp(xi);
 }
 
+// op: 0 se3::exp (6 -> 7), 1 se3::log (7 -> 6), 2 so3::exp (3 -> 4), 3 so3::log (4 -> 3); one thread, f32 like the reference
+__global__ void k_lie(int op, const float* __restrict__ in, float* __restrict__ out) {
+    if (op == 1) {
+        const Pose p{{in[0], in[1], in[2]}, {in[3], in[4], in[5], in[6]}};
+        float xi[6];
+        se3_log(p, xi);
+        for (int a = 0; a < 6; ++a) out[a] = xi[a];
+    } else if (op == 2) {
+        const Quat q = so3_exp(Vec3{in[0], in[1], in[2]});
+        out[0] = q.i; out[1] = q.j; out[2] = q.k; out[3] = q.w;
+    } else if (op == 3) {
+        const Vec3 w = so3_log(Quat{in[0], in[1], in[2], in[3]});
+        out[0] = w.x; out[1] = w.y; out[2] = w.z;
+    }
+}
+
 inline int grid_for(int n, int block, int cap = 148 * 16) { return max(1, min((n + block - 1) / block, cap)); }
 }  // namespace
 
@@ -461,6 +477,10 @@ void launch_h_total(Launcher& L, const Geom& g, const Intrinsics* intr, const ui
 void launch_jacobians(Launcher& L, const uint32_t* pts_level, int n, Intrinsics k, float* out6) {
     if (n <= 0) return;
     k_jacobians<<<(n + 255) / 256, 256, 0, L.stream>>>(pts_level, n, k, out6);
+    ++L.launches;
+}
+void launch_lie(Launcher& L, int op, const float* in, float* out) {
+    k_lie<<<1, 1, 0, L.stream>>>(op, in, out);
     ++L.launches;
 }
 void launch_se3_exp(Launcher& L, const float* xi6, Pose* out) {

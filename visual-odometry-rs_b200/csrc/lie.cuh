@@ -106,6 +106,81 @@ VORS_HD Pose se3_exp(const float xi[6]) {
     return out;
 }
 
+// src/math/so3.rs:61-77 `exp`.
+VORS_HD Quat so3_exp(Vec3 w) {
+    const float theta_2 = w.x * w.x + w.y * w.y + w.z * w.z;
+    float real_factor, imag_factor;
+    if (theta_2 < 1e-2f * 1e-2f) {
+        real_factor = 1.0f - 0.125f * theta_2;
+        imag_factor = 0.5f - (1.0f / 48.0f) * theta_2;
+    } else {
+        const float theta = sqrtf(theta_2);
+        const float half_theta = 0.5f * theta;
+        real_factor = cosf(half_theta);
+        imag_factor = sinf(half_theta) / theta;
+    }
+    const Quat q{imag_factor * w.x, imag_factor * w.y, imag_factor * w.z, real_factor};
+    const float n = sqrtf(quat_norm2(q));
+    return {q.i / n, q.j / n, q.k / n, q.w / n};
+}
+
+// src/math/so3.rs:81-99 `log`.
+VORS_HD Vec3 so3_log(Quat q) {
+    const float imag_norm_2 = q.i * q.i + q.j * q.j + q.k * q.k;
+    const float real_factor = q.w;
+    float f;
+    if (imag_norm_2 < 1e-2f * 1e-2f) {
+        f = 2.0f / real_factor;
+    } else if (fabsf(real_factor) < 1e-2f) {
+        const float imag_norm = sqrtf(imag_norm_2);
+        const float alpha = fabsf(real_factor) / imag_norm;
+        const float theta = copysignf(1.0f, real_factor) * (3.14159265358979323846f - 2.0f * alpha);
+        f = theta / imag_norm;
+    } else {
+        const float imag_norm = sqrtf(imag_norm_2);
+        f = 2.0f * atanf(imag_norm / real_factor) / imag_norm;
+    }
+    return {f * q.i, f * q.j, f * q.k};
+}
+
+// src/math/se3.rs:99-130 `log` (trajectory error metrics; not on the tracking path).
+VORS_HD void se3_log(const Pose& iso, float xi[6]) {
+    const float imag_norm_2 = iso.q.i * iso.q.i + iso.q.j * iso.q.j + iso.q.k * iso.q.k;
+    const float real_factor = iso.q.w;
+    float wx, wy, wz, coef_omega_2;
+    if (imag_norm_2 < 1e-2f * 1e-2f) {
+        const float t = 2.0f / real_factor;
+        wx = t * iso.q.i; wy = t * iso.q.j; wz = t * iso.q.k;
+        const float x_2 = imag_norm_2 / (real_factor * real_factor);
+        coef_omega_2 = (1.0f / 12.0f) * (1.0f + (1.0f / 15.0f) * x_2);
+    } else {
+        const float imag_norm = sqrtf(imag_norm_2);
+        float theta;
+        if (fabsf(real_factor) < 1e-2f) {
+            const float alpha = fabsf(real_factor) / imag_norm;
+            theta = copysignf(1.0f, real_factor) * (3.14159265358979323846f - 2.0f * alpha);
+        } else {
+            theta = 2.0f * atanf(imag_norm / real_factor);
+        }
+        const float theta_2 = theta * theta;
+        const float t = theta / imag_norm;
+        wx = t * iso.q.i; wy = t * iso.q.j; wz = t * iso.q.k;
+        coef_omega_2 = (1.0f - 0.5f * theta * real_factor / imag_norm) / theta_2;
+    }
+    const float w11 = wx * wx, w12 = wx * wy, w13 = wx * wz, w22 = wy * wy, w23 = wy * wz, w33 = wz * wz;
+    const float O[3][3] = {{0.f, -wz, wy}, {wz, 0.f, -wx}, {-wy, wx, 0.f}};
+    const float O2[3][3] = {{-w22 - w33, w12, w13}, {w12, -w11 - w33, w23}, {w13, w23, -w11 - w22}};
+    float V[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) V[r][c] = ((r == c ? 1.0f : 0.0f) - 0.5f * O[r][c]) + coef_omega_2 * O2[r][c];
+    xi[0] = (V[0][0] * iso.t.x + V[0][1] * iso.t.y) + V[0][2] * iso.t.z;
+    xi[1] = (V[1][0] * iso.t.x + V[1][1] * iso.t.y) + V[1][2] * iso.t.z;
+    xi[2] = (V[2][0] * iso.t.x + V[2][1] * iso.t.y) + V[2][2] * iso.t.z;
+    xi[3] = wx; xi[4] = wy; xi[5] = wz;
+}
+
 // nalgebra 0.17 `Matrix6::cholesky()` + `Cholesky::solve` (lm_optimizer.rs:131-134): left-looking
 // LL^T on the lower triangle, fails on a pivot that is not > 0 (zero and NaN), then forward and
 // transposed-back substitution.  A is row-major 6x6 (only the lower triangle is read), b is

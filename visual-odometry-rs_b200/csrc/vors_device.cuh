@@ -151,6 +151,7 @@ void launch_h_total(Launcher& L, const Geom& g, const Intrinsics* intr, const ui
                     double* h_total, const int* items, int m);
 void launch_jacobians(Launcher& L, const uint32_t* pts_level, int n, Intrinsics k, float* out6);
 void launch_se3_exp(Launcher& L, const float* xi6, Pose* out);
+void launch_lie(Launcher& L, int op, const float* in, float* out);
 
 // ---- implemented in dso_kernels.cu ------------------------------------------------------------------
 void launch_sqnorm_direct(Launcher& L, const uint8_t* img, int rows, int cols, int as_magnitude, uint16_t* out);

@@ -125,6 +125,9 @@ SIGNATURES = {
     "vors_align_level": (C.c_int, [_vp, C.c_uint32, _vp, _P(Pose), _P(Pose), _P(C.c_int32), _P(C.c_float), _P(TraceRec), C.c_int, _P(C.c_int)]),
     "vors_align": (C.c_int, [_vp, _vp, C.c_int, _P(Pose), _P(Pose), _P(TrackStats), _P(TraceRec), C.c_int, _P(C.c_int)]),
     "vors_se3_exp": (C.c_int, [_vp, _P(Pose)]),
+    "vors_se3_log": (C.c_int, [_P(Pose), _vp]),
+    "vors_so3_exp": (C.c_int, [_vp, _vp]),
+    "vors_so3_log": (C.c_int, [_vp, _vp]),
 }
 
 _lib = None
@@ -397,6 +400,24 @@ def se3_exp(xi) -> Pose:
     x = np.ascontiguousarray(xi, np.float32)
     _check(load_library().vors_se3_exp(_ptr(x), C.byref(p)))
     return p
+
+
+def se3_log(pose: Pose) -> np.ndarray:
+    xi = np.zeros(6, np.float32)
+    _check(load_library().vors_se3_log(C.byref(pose), _ptr(xi)))
+    return xi
+
+
+def so3_exp(w) -> np.ndarray:
+    q = np.zeros(4, np.float32)
+    _check(load_library().vors_so3_exp(_ptr(np.ascontiguousarray(w, np.float32)), _ptr(q)))
+    return q
+
+
+def so3_log(q) -> np.ndarray:
+    w = np.zeros(3, np.float32)
+    _check(load_library().vors_so3_log(_ptr(np.ascontiguousarray(q, np.float32)), _ptr(w)))
+    return w
 
 
 class Keyframe:
