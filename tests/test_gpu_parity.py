@@ -47,7 +47,7 @@ def _cfgs(vb, oracle, scene, **kw):
 def test_pyramid_gradients_bit_exact(vb, oracle, shape, kind):
     rng = np.random.default_rng(abs(hash((shape, kind))) % 2 ** 32)
     img = _img(rng, shape, kind)
-    for L in (1, 3, 6):
+    for L in (1, 3, 6, 8):  # 8 levels: the fused kernel chains a second launch after 6 halvings
         got = vb.mean_pyramid(img, L)
         ref = oracle.mean_pyramid(img, L)
         assert len(got) == len(ref)

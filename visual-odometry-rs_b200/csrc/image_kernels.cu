@@ -3,6 +3,8 @@
 // All integer stages are bit-exact restatements of the reference semantics (truncating signed
 // division, u16 wrap of `third + thresh`, stable tie-break of the 4-element sort).  Every kernel
 // is batched over streams through blockIdx.y (`items` maps the launch index to the stream slab).
+#include <algorithm>
+
 #include "vors_device.cuh"
 
 namespace vors {
@@ -55,6 +57,48 @@ __global__ void k_halve_mean(const Geom g, int l, uint8_t* __restrict__ pyr_slab
         const uint8_t* p = in + size_t(2 * x) * Rin + 2 * y;
         const unsigned a = p[0], b = p[1], c = p[Rin], d = p[Rin + 1];
         out[o] = uint8_t((a + b + c + d) >> 2);
+    }
+}
+
+// Row A, fused: ALL pyramid levels of a frame in one launch.  One CTA stages a 64x64 level-0 tile in shared memory and
+// halves it in place level by level (up to 6 halvings: 64 -> 1), writing every level's part of the tile; the level-0
+// image is read from HBM exactly once and the per-frame pyramid costs one launch instead of L-1.
+// Floor-halving keeps tiles independent: a level-l pixel exists iff both its children rows/cols exist at level l-1.
+constexpr int kPyrTile = 64;
+__global__ void __launch_bounds__(256) k_pyramid_fused(const Geom g, int l_first, int l_count, uint8_t* __restrict__ pyr_slab,
+                                                        const int* __restrict__ items) {
+    __shared__ uint8_t buf[2][kPyrTile * kPyrTile];  // ping-pong: level l in buf[l & 1], column-major tile (y fastest)
+    uint8_t* pyr = pyr_slab + size_t(item_of(items, blockIdx.z)) * g.pix_total;
+    const int ty0 = blockIdx.x * kPyrTile, tx0 = blockIdx.y * kPyrTile;  // tile origin at level l_first
+    {
+        const uint8_t* in = pyr + g.off[l_first];
+        const int R = g.rows[l_first], C = g.cols[l_first];
+        for (int i = threadIdx.x; i < kPyrTile * kPyrTile; i += blockDim.x) {
+            const int x = i / kPyrTile, y = i - x * kPyrTile;
+            const int gy = ty0 + y, gx = tx0 + x;
+            buf[0][i] = (gy < R && gx < C) ? in[size_t(gx) * R + gy] : uint8_t(0);
+        }
+    }
+    __syncthreads();
+    int side = kPyrTile;
+    for (int k = 1; k <= l_count; ++k) {
+        const int l = l_first + k;
+        const int half = side >> 1;
+        const uint8_t* src = buf[(k - 1) & 1];
+        uint8_t* dst = buf[k & 1];
+        uint8_t* out = pyr + g.off[l];
+        const int R = g.rows[l], C = g.cols[l];
+        const int oy0 = ty0 >> k, ox0 = tx0 >> k;
+        for (int i = threadIdx.x; i < half * half; i += blockDim.x) {
+            const int x = i / half, y = i - x * half;
+            const uint8_t* p = src + (2 * x) * side + 2 * y;
+            const unsigned v = (unsigned(p[0]) + p[1] + p[side] + p[side + 1]) >> 2;  // ((a+b+c+d)/4) as u8, multires.rs:24-29
+            dst[x * half + y] = uint8_t(v);
+            const int gy = oy0 + y, gx = ox0 + x;
+            if (gy < R && gx < C) out[size_t(gx) * R + gy] = uint8_t(v);
+        }
+        __syncthreads();
+        side = half;
     }
 }
 
@@ -423,6 +467,16 @@ void launch_copy_items_u16(Launcher& L, const uint16_t* in, uint16_t* out_slab, 
     ++L.launches;
 }
 void launch_pyramid(Launcher& L, const Geom& g, uint8_t* pyr_slab, const int* items, int m) {
+    // fused: up to 6 halvings per launch (a 64x64 tile collapses to 1 pixel); deeper pyramids chain a second launch
+    for (int l0 = 0; l0 + 1 < g.L; l0 += 6) {
+        const int count = std::min(6, g.L - 1 - l0);
+        dim3 grid((g.rows[l0] + kPyrTile - 1) / kPyrTile, (g.cols[l0] + kPyrTile - 1) / kPyrTile, m);
+        k_pyramid_fused<<<grid, 256, 0, L.stream>>>(g, l0, count, pyr_slab, items);
+        ++L.launches;
+    }
+}
+// one level at a time (kept for comparison / debugging)
+void launch_pyramid_levelwise(Launcher& L, const Geom& g, uint8_t* pyr_slab, const int* items, int m) {
     for (int l = 1; l < g.L; ++l) {
         dim3 grid(grid_for(g.rows[l] * g.cols[l], 256), m);
         k_halve_mean<<<grid, 256, 0, L.stream>>>(g, l, pyr_slab, items);
