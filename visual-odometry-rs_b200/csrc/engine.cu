@@ -112,6 +112,7 @@ class Engine {
     uint8_t* d_mask = nullptr;       // coarse-to-fine masks of all levels
     float* d_idepth = nullptr;       // idepth pyramid maps (NaN = unknown)
     float* d_weight = nullptr;
+    uint32_t* d_defer = nullptr;     // align kernel's deferred-slot bitmaps, pt_total / 32 words per stream
     uint32_t* d_pts = nullptr;       // chunk-blocked candidates, 3 * pt_total words per stream
     int* d_blk_count = nullptr;
     int* d_n_points = nullptr;       // [n][kMaxLevels]
@@ -145,7 +146,7 @@ class Engine {
     void destroy() {
         DeviceScope scope(device);
         if (L.stream) cudaStreamSynchronize(L.stream);
-        void* dev_ptrs[] = {d_pyr, d_stage8, d_stage16, d_depth, d_grad, d_g2, d_mask, d_idepth, d_weight, d_pts,
+        void* dev_ptrs[] = {d_pyr, d_stage8, d_stage16, d_depth, d_grad, d_g2, d_mask, d_idepth, d_weight, d_pts, d_defer,
                             d_blk_count, d_n_points, d_h_total, d_items, d_jobs, d_init, d_results, d_scratch, d_trace, d_tmp, d_gradmag, d_dso_ws};
         for (void* p : dev_ptrs)
             if (p) cudaFree(p);
@@ -204,7 +205,7 @@ class Engine {
             g.off[l] = off;
             g.blk_off[l] = boff;
             g.pt_off[l] = poff;
-            poff += (g.rows[l] * g.cols[l] + kChunk - 1) / kChunk * kChunk;
+            poff += (g.rows[l] * g.cols[l] + kPtAlign - 1) / kPtAlign * kPtAlign;
             off += g.rows[l] * g.cols[l];
             boff += (g.rows[l] * g.cols[l] + kCompactBlock - 1) / kCompactBlock;
             intr[l] = k;  // camera.rs:106-108 `multi_res`
@@ -212,6 +213,7 @@ class Engine {
         }
         for (int l = levels; l <= kMaxLevels; ++l) g.blk_off[l] = boff;
         g.pix_total = off;
+        g.pix_stride = (off + g.rows[0] + 2 + 15) / 16 * 16;  // + zero page (vors_device.cuh)
         g.pt_total = poff;
         g.blk_total = boff;
 
@@ -222,8 +224,9 @@ class Engine {
         CU_TRY(align_query(&info));
         if (info.max_resident_ctas < 1) return fail(VORS_E_CUDA, "align kernel cannot be resident on this device");
 
-        const size_t N = size_t(n), P = size_t(g.pix_total), I = size_t(rows) * cols, PT = size_t(g.pt_total);
+        const size_t N = size_t(n), P = size_t(g.pix_stride), I = size_t(rows) * cols, PT = size_t(g.pt_total);
         CU_TRY(cudaMalloc(&d_pyr, N * P));
+        CU_TRY(cudaMemsetAsync(d_pyr, 0, N * P, L.stream));  // the zero page of every slab stays zero: no kernel writes it
         CU_TRY(cudaMalloc(&d_stage8, N * I));
         CU_TRY(cudaMalloc(&d_stage16, N * I * 2));
         CU_TRY(cudaMalloc(&d_depth, N * I * 2));
@@ -233,6 +236,8 @@ class Engine {
         CU_TRY(cudaMalloc(&d_idepth, N * P * 4));
         CU_TRY(cudaMalloc(&d_weight, N * P * 4));
         CU_TRY(cudaMalloc(&d_pts, N * PT * 12));
+        CU_TRY(cudaMalloc(&d_defer, N * PT / 8));
+        CU_TRY(cudaMemsetAsync(d_defer, 0, N * PT / 8, L.stream));  // the align kernel leaves it all-zero after every pass
         // a partial last chunk is staged whole: keep its padding initialised
         CU_TRY(cudaMemsetAsync(d_pts, 0, N * PT * 12, L.stream));
         CU_TRY(cudaMalloc(&d_blk_count, N * size_t(g.blk_total) * 4));
@@ -269,16 +274,20 @@ class Engine {
 
     void fill_job(AlignJob& j, int stream, int lvl_first, int lvl_last, int flow_level, int pass_only) const {
         std::memset(&j, 0, sizeof(j));
-        const size_t base = size_t(stream) * g.pix_total;
+        const size_t base = size_t(stream) * g.pix_stride;
         const size_t pbase = size_t(stream) * g.pt_total;
         for (int l = 0; l < g.L; ++l) {
             LevelJob& lj = j.lv[l];
             lj.pts = d_pts + 3 * (pbase + g.pt_off[l]);
+            lj.defer = d_defer + (pbase + g.pt_off[l]) / 32;
             lj.img = d_pyr + base + g.off[l];
             lj.n_ptr = d_n_points + stream * kMaxLevels + l;
             lj.h_total = d_h_total + (size_t(stream) * kMaxLevels + l) * kHStride;
             lj.rows = g.rows[l];
             lj.cols = g.cols[l];
+            const int zoff = g.pix_total - g.off[l];  // from this level's image to the slab's zero page
+            lj.zero_u = float(zoff / g.rows[l]);
+            lj.zero_v = float(zoff % g.rows[l]);
             lj.k = intr[l];
         }
         j.lvl_first = lvl_first;
@@ -293,13 +302,13 @@ class Engine {
         const size_t I = size_t(rows) * cols;
         bool contiguous = true;
         for (int i = 1; i < m && contiguous; ++i) contiguous = (img[start + i] == img[start] + size_t(i) * I);
-        uint8_t* pyr0 = d_pyr + size_t(start) * g.pix_total;
+        uint8_t* pyr0 = d_pyr + size_t(start) * g.pix_stride;
         if (layout == VORS_COL_MAJOR) {
             if (contiguous) {
-                CU_TRY(cudaMemcpy2DAsync(pyr0, size_t(g.pix_total), img[start], I, I, size_t(m), cudaMemcpyHostToDevice, X.stream));
+                CU_TRY(cudaMemcpy2DAsync(pyr0, size_t(g.pix_stride), img[start], I, I, size_t(m), cudaMemcpyHostToDevice, X.stream));
             } else {
                 for (int i = 0; i < m; ++i)
-                    CU_TRY(cudaMemcpyAsync(pyr0 + size_t(i) * g.pix_total, img[start + i], I, cudaMemcpyHostToDevice, X.stream));
+                    CU_TRY(cudaMemcpyAsync(pyr0 + size_t(i) * g.pix_stride, img[start + i], I, cudaMemcpyHostToDevice, X.stream));
             }
         } else {
             uint8_t* stage = d_stage8 + size_t(start) * I;
@@ -309,7 +318,7 @@ class Engine {
                 for (int i = 0; i < m; ++i)
                     CU_TRY(cudaMemcpyAsync(stage + size_t(i) * I, img[start + i], I, cudaMemcpyHostToDevice, X.stream));
             }
-            launch_transpose_u8(X, stage, pyr0, size_t(g.pix_total), nullptr, m, rows, cols);
+            launch_transpose_u8(X, stage, pyr0, size_t(g.pix_stride), nullptr, m, rows, cols);
         }
         return VORS_OK;
     }
@@ -317,7 +326,7 @@ class Engine {
 
     int upload_images_device(const uint8_t* img_dev) {  // column-major, n*rows*cols contiguous
         const size_t I = size_t(rows) * cols;
-        CU_TRY(cudaMemcpy2DAsync(d_pyr, size_t(g.pix_total), img_dev, I, I, size_t(n), cudaMemcpyDeviceToDevice, L.stream));
+        CU_TRY(cudaMemcpy2DAsync(d_pyr, size_t(g.pix_stride), img_dev, I, I, size_t(n), cudaMemcpyDeviceToDevice, L.stream));
         return VORS_OK;
     }
 
@@ -346,9 +355,9 @@ class Engine {
             // sqrt(squared_norm_direct) as u16, nb_iterations_left = 2), one stream at a time (host-driven recursion)
             for (int j = 0; j < m; ++j) {
                 const int s = h_items[j];
-                launch_sqnorm_direct(L, d_pyr + size_t(s) * g.pix_total, rows, cols, 1, d_gradmag);
+                launch_sqnorm_direct(L, d_pyr + size_t(s) * g.pix_stride, rows, cols, 1, d_gradmag);
                 const int rc = dso_select_device(L, d_gradmag, rows, cols, int(cfg.dso_nb_target ? cfg.dso_nb_target : 2000), 2,
-                                                 0x9E3779B97F4A7C15ull, d_mask + size_t(s) * g.pix_total, d_dso_ws, h_dso_flags,
+                                                 0x9E3779B97F4A7C15ull, d_mask + size_t(s) * g.pix_stride, d_dso_ws, h_dso_flags,
                                                  nullptr, nullptr);
                 if (rc != VORS_OK) return fail(rc, "DSO candidate selection failed");
             }
@@ -498,7 +507,7 @@ class Engine {
             for (int c = 0; c < n_chunks; ++c) {
                 const int start = c * (n / 2), m = c == 0 ? n / 2 : n - n / 2;
                 CU_TRY(cudaStreamWaitEvent(L.stream, ev_up[c], 0));
-                launch_pyramid(L, g, d_pyr + size_t(start) * g.pix_total, nullptr, m);
+                launch_pyramid(L, g, d_pyr + size_t(start) * g.pix_stride, nullptr, m);
                 if ((rc = run_align(m, max_points, start)) != VORS_OK) return rc;
             }
         }
@@ -985,13 +994,14 @@ int vors_keyframe_points(const vors_keyframe* kf, uint32_t level, uint32_t* xy, 
     }
     for (int i = 0; i < np; ++i) {
         if (xy) {
-            xy[2 * i] = pk[size_t(i)] & 0xFFFu;
-            xy[2 * i + 1] = (pk[size_t(i)] >> 12) & 0xFFFu;
+            xy[2 * i] = rec_x(pk[size_t(i)]);
+            xy[2 * i + 1] = rec_y(pk[size_t(i)]);
         }
-        if (tmpl) tmpl[i] = uint8_t(pk[size_t(i)] >> 24);
-        if (grad_xy) {
-            grad_xy[2 * i] = int16_t(gr[size_t(i)] & 0xFFFFu);
-            grad_xy[2 * i + 1] = int16_t(gr[size_t(i)] >> 16);
+        if (tmpl) tmpl[i] = uint8_t(rec_tmpl(pk[size_t(i)]));
+        if (grad_xy) {  // half2(gx, gy): small integers, exact
+            const __half2 h = *reinterpret_cast<const __half2*>(&gr[size_t(i)]);
+            grad_xy[2 * i] = int16_t(__low2float(h));
+            grad_xy[2 * i + 1] = int16_t(__high2float(h));
         }
     }
     return VORS_OK;

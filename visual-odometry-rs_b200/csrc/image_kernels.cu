@@ -47,7 +47,7 @@ __global__ void k_copy_items_u16(const uint16_t* __restrict__ in, uint16_t* __re
 // Row A: one level of `multires::mean_pyramid` (multires.rs:21-31): ((a+b+c+d)/4) as u8 over 2x2
 // blocks a=(2i,2j) b=(2i+1,2j) c=(2i,2j+1) d=(2i+1,2j+1); odd last row/col dropped.
 __global__ void k_halve_mean(const Geom g, int l, uint8_t* __restrict__ pyr_slab, const int* __restrict__ items) {
-    uint8_t* pyr = pyr_slab + size_t(item_of(items, blockIdx.y)) * g.pix_total;
+    uint8_t* pyr = pyr_slab + size_t(item_of(items, blockIdx.y)) * g.pix_stride;
     const uint8_t* in = pyr + g.off[l - 1];
     uint8_t* out = pyr + g.off[l];
     const int R = g.rows[l], C = g.cols[l], Rin = g.rows[l - 1];
@@ -68,7 +68,7 @@ constexpr int kPyrTile = 64;
 __global__ void __launch_bounds__(256) k_pyramid_fused(const Geom g, int l_first, int l_count, uint8_t* __restrict__ pyr_slab,
                                                         const int* __restrict__ items) {
     __shared__ uint8_t buf[2][kPyrTile * kPyrTile];  // ping-pong: level l in buf[l & 1], column-major tile (y fastest)
-    uint8_t* pyr = pyr_slab + size_t(item_of(items, blockIdx.z)) * g.pix_total;
+    uint8_t* pyr = pyr_slab + size_t(item_of(items, blockIdx.z)) * g.pix_stride;
     const int ty0 = blockIdx.x * kPyrTile, tx0 = blockIdx.y * kPyrTile;  // tile origin at level l_first
     {
         const uint8_t* in = pyr + g.off[l_first];
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) k_pyramid_fused(const Geom g, int l_first
 // g2 = (gx*gx + gy*gy) as u16 (gradient.rs:38-44).
 __global__ void k_gradients(const Geom g, const uint8_t* __restrict__ pyr_slab, uint32_t* __restrict__ grad_slab,
                             uint16_t* __restrict__ g2_slab, const int* __restrict__ items) {
-    const size_t base = size_t(item_of(items, blockIdx.y)) * g.pix_total;
+    const size_t base = size_t(item_of(items, blockIdx.y)) * g.pix_stride;
     const uint8_t* pyr = pyr_slab + base;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.pix_total; i += gridDim.x * blockDim.x) {
         int l = 0;
@@ -150,7 +150,7 @@ __device__ __forceinline__ void cswap(unsigned& a, unsigned& b) {
 
 __global__ void k_c2f_level(const Geom g, int l, uint16_t thresh, const uint16_t* __restrict__ g2_slab,
                             uint8_t* __restrict__ mask_slab, const int* __restrict__ items) {
-    const size_t base = size_t(item_of(items, blockIdx.y)) * g.pix_total;
+    const size_t base = size_t(item_of(items, blockIdx.y)) * g.pix_stride;
     const uint16_t* g2 = g2_slab + base + g.off[l];
     uint8_t* mask = mask_slab + base + g.off[l];
     const uint8_t* pre = (l + 1 == g.L - 1) ? nullptr : mask_slab + base + g.off[l + 1];  // coarsest: all true
@@ -185,7 +185,7 @@ __global__ void k_idepth0(const Geom g, const uint16_t* __restrict__ depth_slab,
                           const uint8_t* __restrict__ mask_slab, int dense, float scale, float variance,
                           float* __restrict__ idepth_slab, float* __restrict__ weight_slab, const int* __restrict__ items) {
     const int it = item_of(items, blockIdx.y);
-    const size_t base = size_t(it) * g.pix_total;
+    const size_t base = size_t(it) * g.pix_stride;
     const uint16_t* depth = depth_slab + size_t(it) * depth_stride;
     const int n = g.rows[0] * g.cols[0];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -201,7 +201,7 @@ __global__ void k_idepth0(const Geom g, const uint16_t* __restrict__ depth_slab,
 // to right in f32; one known child is copied verbatim; none -> Unknown.
 __global__ void k_idepth_halve(const Geom g, int l, float* __restrict__ idepth_slab, float* __restrict__ weight_slab,
                                const int* __restrict__ items) {
-    const size_t base = size_t(item_of(items, blockIdx.y)) * g.pix_total;
+    const size_t base = size_t(item_of(items, blockIdx.y)) * g.pix_stride;
     const float* din = idepth_slab + base + g.off[l - 1];
     const float* win = weight_slab + base + g.off[l - 1];
     float* dout = idepth_slab + base + g.off[l];
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(kCompactBlock) k_compact_count(const Geom g, c
     const int l = level_of_block(g, blk);
     const int i = (blk - g.blk_off[l]) * kCompactBlock + threadIdx.x;
     const int n = g.rows[l] * g.cols[l];
-    const bool known = (i < n) && !isnan(idepth_slab[size_t(it) * g.pix_total + g.off[l] + i]);
+    const bool known = (i < n) && !isnan(idepth_slab[size_t(it) * g.pix_stride + g.off[l] + i]);
     const int c = __syncthreads_count(known);
     if (threadIdx.x == 0) blk_count[size_t(it) * g.blk_total + blk] = c;
 }
@@ -308,12 +308,15 @@ __global__ void __launch_bounds__(1024) k_compact_scan(const Geom g, int* __rest
         __syncthreads();
     }
     if (threadIdx.x == 0) n_points[it * kMaxLevels + l] = carry;
-    // zero the padding of the last (partial) chunk: the align kernel stages whole chunks and relies on padding
-    // candidates being (pk, idepth, grad) = 0 -> finite arithmetic and exactly zero contributions
-    const int total = carry, padded = (total + kChunk - 1) / kChunk * kChunk;
+    // padding up to the next whole ring stage of the align kernel: (pk, idepth, grad) = (0, NaN, 0).  A NaN inverse
+    // depth fails the kernel's inside test, which sends the slot to its rare path where padding is recognised by index.
+    const int total = carry, padded = (total + kPtAlign - 1) / kPtAlign * kPtAlign;
     uint32_t* lvl = pts_slab + 3 * (size_t(it) * g.pt_total + g.pt_off[l]);
-    for (int i = total + threadIdx.x; i < padded; i += blockDim.x)
-        for (int f = 0; f < 3; ++f) lvl[pt_word(i, f)] = 0u;
+    for (int i = total + threadIdx.x; i < padded; i += blockDim.x) {
+        lvl[pt_word(i, 0)] = 0u;
+        lvl[pt_word(i, 1)] = 0x7FC00000u;
+        lvl[pt_word(i, 2)] = 0u;
+    }
 }
 
 __global__ void __launch_bounds__(kCompactBlock) k_compact_scatter(const Geom g, const float* __restrict__ idepth_slab,
@@ -323,7 +326,7 @@ __global__ void __launch_bounds__(kCompactBlock) k_compact_scatter(const Geom g,
                                                                    const int* __restrict__ items) {
     __shared__ int warp_cnt[32];
     const int it = item_of(items, blockIdx.y);
-    const size_t base = size_t(it) * g.pix_total;
+    const size_t base = size_t(it) * g.pix_stride;
     const int blk = blockIdx.x;
     const int l = level_of_block(g, blk);
     const int i = (blk - g.blk_off[l]) * kCompactBlock + threadIdx.x;
@@ -355,9 +358,9 @@ __global__ void __launch_bounds__(kCompactBlock) k_compact_scatter(const Geom g,
         const int pos = blk_base[size_t(it) * g.blk_total + blk] + warp_cnt[w] + __popc(ballot & ((1u << lane) - 1u));
         const int x = i / R, y = i - x * R;
         uint32_t* lvl = pts_slab + 3 * (size_t(it) * g.pt_total + g.pt_off[l]);
-        lvl[pt_word(pos, 0)] = uint32_t(x) | (uint32_t(y) << 12) | (uint32_t(pyr_slab[src]) << 24);
+        lvl[pt_word(pos, 0)] = rec_pack_pk(x, y, uint32_t(pyr_slab[src]));
         lvl[pt_word(pos, 1)] = __float_as_uint(d);
-        lvl[pt_word(pos, 2)] = grad_slab[src];
+        lvl[pt_word(pos, 2)] = rec_pack_grad(grad_slab[src]);
     }
 }
 
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(512) k_h_total(const Geom g, const LevelIntrin
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const uint32_t p = lvl[pt_word(i, 0)], gr = lvl[pt_word(i, 2)];
         float J[6];
-        jacobian_at<true>(float(int16_t(gr & 0xFFFFu)), float(int16_t(gr >> 16)), float(p & 0xFFFu), float((p >> 12) & 0xFFFu),
+        jacobian_at<true>(rec_gx(gr), rec_gy(gr), float(rec_x(p)), float(rec_y(p)),
                           __uint_as_float(lvl[pt_word(i, 1)]), k, J);
         int t = 0;
 #pragma unroll
@@ -416,7 +419,7 @@ __global__ void k_jacobians(const uint32_t* __restrict__ lvl, int n, Intrinsics 
     if (i >= n) return;
     const uint32_t p = lvl[pt_word(i, 0)], gr = lvl[pt_word(i, 2)];
     float J[6];
-    jacobian_at<true>(float(int16_t(gr & 0xFFFFu)), float(int16_t(gr >> 16)), float(p & 0xFFFu), float((p >> 12) & 0xFFFu),
+    jacobian_at<true>(rec_gx(gr), rec_gy(gr), float(rec_x(p)), float(rec_y(p)),
                       __uint_as_float(lvl[pt_word(i, 1)]), k, J);
 #pragma unroll
     for (int a = 0; a < 6; ++a) out6[size_t(i) * 6 + a] = J[a];

@@ -223,7 +223,11 @@ VORS_HD Intrinsics half_res(const Intrinsics& k) {
 // folded into one 3x4 matrix acting on (x, y, 1, idepth):
 //   [U V W]^T = K (R K^-1 [x y 1]^T + idepth * t),   u = U / W,  v = V / W.
 // Built in f64 from the f32 model so the folding itself adds no error, stored as f32.
-VORS_HD void warp_matrix(const Pose& m, const Intrinsics& k, float M[12]) {
+// `centred` = true builds the matrix that maps (x - cx, y - cy, 1, idepth) to (U - cx W, V - cy W, W) instead, so that
+// u = cx + Uc / W: the align kernel feeds it the rounded differences the reference itself starts from
+// (camera.rs:135-140 `back_project`) and adds the principal point last (camera.rs:126-132 `project`).  No entry of
+// that matrix carries the ~cx-sized constant whose f32 rounding would shift every warped pixel by the same 1e-5 px.
+VORS_HD void warp_matrix(const Pose& m, const Intrinsics& k, float M[12], bool centred = false) {
     const double qi = m.q.i, qj = m.q.j, qk = m.q.k, qw = m.q.w;
     // rotation matrix of the (possibly slightly non-unit) quaternion exactly as quat_rotate applies it:
     // p + 2 w (v x p) + 2 v x (v x p)
@@ -232,15 +236,17 @@ VORS_HD void warp_matrix(const Pose& m, const Intrinsics& k, float M[12]) {
                             {2.0 * (qi * qk - qj * qw), 2.0 * (qj * qk + qi * qw), 1.0 - 2.0 * (qi * qi + qj * qj)}};
     const double fx = k.fx, fy = k.fy, cx = k.cx, cy = k.cy, s = k.s;
     // K^-1 columns: ray(x, y) = ((x - cx - s (y - cy) / fy) / fx, (y - cy) / fy, 1)
-    const double Ki[3][3] = {{1.0 / fx, -s / (fx * fy), (s * cy / fy - cx) / fx}, {0.0, 1.0 / fy, -cy / fy}, {0.0, 0.0, 1.0}};
+    const double Ki[3][3] = {{1.0 / fx, -s / (fx * fy), centred ? 0.0 : (s * cy / fy - cx) / fx},
+                             {0.0, 1.0 / fy, centred ? 0.0 : -cy / fy},
+                             {0.0, 0.0, 1.0}};
     double RK[3][3];
     for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) RK[r][c] = R[r][0] * Ki[0][c] + R[r][1] * Ki[1][c] + R[r][2] * Ki[2][c];
     const double t[3] = {m.t.x, m.t.y, m.t.z};
     for (int c = 0; c < 4; ++c) {
         const double a0 = c < 3 ? RK[0][c] : t[0], a1 = c < 3 ? RK[1][c] : t[1], a2 = c < 3 ? RK[2][c] : t[2];
-        M[0 * 4 + c] = float(fx * a0 + s * a1 + cx * a2);
-        M[1 * 4 + c] = float(fy * a1 + cy * a2);
+        M[0 * 4 + c] = float(fx * a0 + s * a1 + (centred ? 0.0 : cx * a2));
+        M[1 * 4 + c] = float(fy * a1 + (centred ? 0.0 : cy * a2));
         M[2 * 4 + c] = float(a2);
     }
 }

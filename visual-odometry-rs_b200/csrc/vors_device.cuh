@@ -3,12 +3,18 @@
 // HBM layout (everything column-major like nalgebra::DMatrix: pixel (row y, col x) at x*rows + y):
 //   * an image pyramid is one slab of `pix_total` elements, level l at pixel offset off[l];
 //   * a keyframe's candidate points are three 4-byte streams per level in the reference's scan order
-//     (extract_z, inverse_compositional.rs:260-279), stored at 256-byte aligned offsets pt_off[l] with capacity
-//     rows_l*cols_l (so the align kernel can stage them with 16-byte aligned bulk copies):  pk = x | y<<12 | template<<24,  idepth (f32),  grad = gx(i16) | gy(i16)<<16.
-//     12 B per candidate; the align kernel recomputes the Jacobian and J J^T in registers.
-//   * n streams (trackers) of a batch own consecutive slabs: base + stream * pix_total (pt_total for candidates).
+//     (extract_z, inverse_compositional.rs:260-279), chunk-blocked (64 candidates = one 768-byte record
+//     pk[64] | idepth[64] | grad[64]) at offsets pt_off[l] aligned to kPtAlign candidates with capacity rows_l*cols_l,
+//     so the align kernel stages whole ring stages with 16-byte aligned bulk copies:
+//     pk = x | y<<12 | template<<24,  idepth (f32),  grad = half2(gx, gy) (integers |g| <= 255: exact in f16).
+//     Padding up to the next kPtAlign multiple is (0, NaN, 0): a NaN inverse depth can never pass the align
+//     kernel's inside test.  12 B per candidate; the align kernel recomputes the Jacobian and J J^T in registers.
+//   * n streams (trackers) of a batch own consecutive slabs: base + stream * pix_stride (pt_total for candidates);
+//     pix_stride = pix_total + a zero page of rows_0 + 2 bytes (rounded up to 16) that is never written in the
+//     frame-pyramid slab: the align kernel points candidates that fall outside the frame at it (all four texels 0).
 #pragma once
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -21,20 +27,36 @@ constexpr int kMaxLevels = VORS_MAX_LEVELS;
 constexpr int kCompactBlock = 1024;  // elements per ordered-compaction block
 constexpr int kTraceCap = 256;       // trace records kept per alignment
 constexpr int kMaxTeam = 160;        // CTAs cooperating on one alignment (<= one per SM)
-constexpr int kChunk = 64;          // candidates per warp-stage of the align kernel's TMA ring (256 B per stream)
+constexpr int kChunk = 64;          // candidates per chunk-blocked record (768 B)
+constexpr int kPtAlign = 128;        // a level's candidate block is padded to this many candidates (one align-kernel ring stage)
 constexpr int kHStride = 24;         // doubles per (stream, level) in the H_total table (21 used)
-constexpr int kNumAcc = 29;          // sum r^2, n_inside, g[6], H[21] (upper triangle)
+constexpr int kNumAcc = 29;          // finished pass: sum r^2, n_inside, g[6], H[21] (upper triangle)
+constexpr int kNumRaw = 34;          // raw pass accumulators: sum r^2, n_inside, 11 gradient moments (or g[6]), H_outside[21]
 
 struct Geom {
     int L;
     int rows[kMaxLevels], cols[kMaxLevels];
     int off[kMaxLevels];         // pixel offset of level l inside a slab
-    int pt_off[kMaxLevels];      // element offset of level l inside a candidate-stream slab (kChunk-aligned for TMA)
-    int pt_total;                // candidate-stream slab extent per stream (kChunk-aligned)
+    int pt_off[kMaxLevels];      // element offset of level l inside a candidate-stream slab (kPtAlign-aligned for TMA)
+    int pt_total;                // candidate-stream slab extent per stream (kPtAlign-aligned)
     int blk_off[kMaxLevels + 1]; // compaction-block offset of level l (kCompactBlock px per block)
-    int pix_total;
+    int pix_total;               // pixels of all levels
+    int pix_stride;              // per-stream slab stride: pix_total + zero page (see above)
     int blk_total;
 };
+
+// ---- candidate record fields -----------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t rec_pack_pk(int x, int y, uint32_t tmpl) { return uint32_t(x) | (uint32_t(y) << 12) | (tmpl << 24); }
+__host__ __device__ __forceinline__ uint32_t rec_x(uint32_t pk) { return pk & 0xFFFu; }
+__host__ __device__ __forceinline__ uint32_t rec_y(uint32_t pk) { return (pk >> 12) & 0xFFFu; }
+__host__ __device__ __forceinline__ uint32_t rec_tmpl(uint32_t pk) { return pk >> 24; }
+// gradient word: i16 pair of the gradient slab (gx | gy<<16) -> half2(gx, gy)
+__device__ __forceinline__ uint32_t rec_pack_grad(uint32_t grad_i16x2) {
+    const __half2 h = __floats2half2_rn(float(int(short(grad_i16x2 & 0xFFFFu))), float(int(short(grad_i16x2 >> 16))));
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float rec_gx(uint32_t gr) { return __half2float(__ushort_as_half((unsigned short)(gr & 0xFFFFu))); }
+__device__ __forceinline__ float rec_gy(uint32_t gr) { return __half2float(__ushort_as_half((unsigned short)(gr >> 16))); }
 
 // One pyramid level of one alignment, as the align kernel sees it.
 // word index of field f (0 pk, 1 idepth, 2 grad) of candidate i inside a level's chunk-blocked block
@@ -45,7 +67,9 @@ struct LevelJob {
     const uint8_t* img;  // current frame, this level
     const int* n_ptr;    // number of candidates (device memory: written by the compaction kernels)
     const double* h_total;  // sum over ALL candidates of J J^T, 21 upper-triangle entries (k_h_total)
+    uint32_t* defer;     // bitmap of the level's candidate slots the align kernel's hot loop deferred (all zero between passes)
     int rows, cols;
+    float zero_u, zero_v;  // integer-valued image coordinates whose 2x2 footprint is the slab's zero page
     Intrinsics k;
 };
 
@@ -75,7 +99,7 @@ struct AlignResult {
 };
 
 struct TeamScratch {
-    double part[2][kMaxTeam][32];
+    double part[2][kMaxTeam][40];
     unsigned int counter;
     unsigned int pad[31];
 };
@@ -100,9 +124,14 @@ struct AlignParams {
 // reciprocal).  kSkew = false is the zero-skew specialisation (every intrinsics set the reference ships,
 // src/dataset/tum_rgbd.rs:23-51, has skew 0): algebraically identical, 7 fewer instructions.
 template <bool kSkew = true>
+__device__ __forceinline__ void jacobian_centred(float gu, float gv, float a, float b, float rho, const Intrinsics& k, float J[6]);
+template <bool kSkew = true>
 __device__ __forceinline__ void jacobian_at(float gu, float gv, float u, float v, float rho, const Intrinsics& k, float J[6]) {
-    const float a = u - k.cx;
-    const float b = v - k.cy;
+    jacobian_centred<kSkew>(gu, gv, u - k.cx, v - k.cy, rho, k, J);
+}
+// same, from a = u - cu, b = v - cv
+template <bool kSkew>
+__device__ __forceinline__ void jacobian_centred(float gu, float gv, float a, float b, float rho, const Intrinsics& k, float J[6]) {
     const float _fv = 1.0f / k.fy;
     const float _fu = 1.0f / k.fx;
     if (kSkew) {
