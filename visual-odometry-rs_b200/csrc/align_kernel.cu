@@ -4,17 +4,18 @@
 // walks the pyramid coarse to fine and, per level, runs the reference's Levenberg-Marquardt loop
 // (src/math/optimizer.rs:57-70 + src/core/track/lm_optimizer.rs:113-192) entirely on the device:
 //
-//   pass      warp-specialised.  A PRODUCER warp stages the level's three candidate streams (12 B per
-//             candidate) into shared memory with TMA bulk copies (cp.async.bulk, SASS UBLKCP) through a
-//             full/empty mbarrier ring of kStages x 64 candidates per consumer warp, so HBM latency is
-//             covered by ~74 KB in flight per SM instead of by occupancy.  Eight CONSUMER warps evaluate
-//             two candidates per lane per stage, branch-free: warp with the folded 3x4 matrix of lie.cuh
-//             (lm_optimizer.rs:213-219), the reference's conservative inside rule, f32 bilinear sample of
-//             u8 texels (lm_optimizer.rs:227-251), residual against the template value, Jacobian recomputed
-//             in registers (inverse_compositional.rs:313-341), and sum r^2, n_inside, g = sum J r.
-//             H = sum J J^T over the inside set is formed as H_total - H_outside: H_total is precomputed per
-//             keyframe level (k_h_total), so only candidates that fall outside accumulate J J^T, under a
-//             warp-uniform branch (eval_energy + compute_eval_data, lm_optimizer.rs:68-107, fused);
+//   pass      every warp streams its share of the level's candidate records (12 B per candidate, 128 candidates per
+//             stage) through its own shared-memory ring with TMA bulk copies (cp.async.bulk, SASS UBLKCP) issued
+//             kStages - 1 stages ahead, so HBM latency is covered by bytes in flight instead of by occupancy, and
+//             evaluates four candidates per lane per stage, branch-free on the common path: warp with the folded
+//             3x4 matrix of lie.cuh (lm_optimizer.rs:213-219), inside test with a safety margin, f32 bilinear sample
+//             of u8 texels (lm_optimizer.rs:227-251), residual against the template value, sum r^2 and eleven
+//             moments of (gu r, gv r) from which g = sum J r is assembled once per pass (inverse_compositional.rs:
+//             313-341; J itself is never formed on the common path).  Candidates that fall outside read a zero page
+//             (exact zero contributions) and add J J^T to per-thread shared-memory sums: H over the inside set is
+//             H_total - H_outside, H_total precomputed per keyframe level (k_h_total).  Slots within 1/128 px of an
+//             inside-test boundary are deferred through a bitmap and re-evaluated after the hot loop with the
+//             reference's own operation order (eval_energy + compute_eval_data, lm_optimizer.rs:68-107, fused);
 //   reduce    warp shuffles -> shared memory -> f64 per-CTA partials -> (team > 1) peer partials
 //             through global memory with one counter barrier per pass; fixed order => deterministic;
 //   decide    thread 0 of every CTA redundantly replays accept / reject / stop (lm_optimizer.rs:
@@ -24,9 +25,10 @@
 //
 // team == 1 is the throughput configuration (one alignment per CTA, two CTAs per SM so one CTA's
 // serial solve overlaps the other's pass); team > 1 trades efficiency for latency on few streams.
-// No tensor cores: the work is ~130 scalar f32 instructions per 12-byte candidate, bounded by
+// No tensor cores: the work is ~90 scalar f32 instructions per 12-byte candidate, bounded by
 // instruction issue, not by a dense contraction.
 #include <cooperative_groups.h>
+#include <cstdio>
 
 #include "vors_device.cuh"
 
@@ -34,13 +36,35 @@ namespace vors {
 
 namespace {
 
-constexpr int kWarps = 9;                     // consumer warps per CTA (+ 1 producer warp = 10 warps)
+#ifndef VORS_PIPE
+#define VORS_PIPE 0      // 0: back(q) after front(q+1) (longest gather-to-use distance, measured best); 1: between its two halves
+#endif
+#ifndef VORS_TIMING
+#define VORS_TIMING 0
+#endif
+#ifndef VORS_TOUCH
+#define VORS_TOUCH 0
+#endif
+#ifndef VORS_EXPERIMENT
+#define VORS_EXPERIMENT 0
+#endif
+#ifndef VORS_WARPS
+#define VORS_WARPS 10
+#endif
+#ifndef VORS_MIN_CTAS
+#define VORS_MIN_CTAS 2
+#endif
+#ifndef VORS_STAGES
+#define VORS_STAGES 2
+#endif
+constexpr int kWarps = VORS_WARPS;            // warps per CTA; every warp refills its own TMA ring
 constexpr int kConsumers = kWarps * 32;
-constexpr int kBlock = kConsumers + 32;       // + one producer warp
-constexpr int kMinCtasPerSm = 2;              // register cap 96: 20 warps per SM
-constexpr int kStageChunks = 2;               // chunk-blocked records per ring stage
-constexpr int kStageCand = kStageChunks * kChunk;  // 128 candidates = 4 per lane per stage (== kPtAlign)
-constexpr int kStages = 3;                    // TMA ring depth per consumer warp
+constexpr int kBlock = kConsumers;
+constexpr int kMinCtasPerSm = VORS_MIN_CTAS;  // 10 warps x 2 CTAs: register cap 96, 20 warps per SM
+constexpr int kStageChunks = VORS_STAGE_CHUNKS;  // chunk-blocked records per ring stage
+constexpr int kStageCand = kStageChunks * kChunk;  // candidates per stage, 2 per lane per chunk (== kPtAlign)
+constexpr int kStageWordsBm = kStageCand / 32;     // bitmap words per stage
+constexpr int kStages = VORS_STAGES;          // TMA ring depth per warp
 constexpr int kStageWords = kStageChunks * 3 * kChunk;  // per chunk: pk[64] | idepth[64] | grad[64]
 constexpr uint32_t kStageBytes = kStageWords * 4;
 constexpr int kHsmStride = 28;
@@ -64,14 +88,19 @@ struct LmShared {
     int trace_len;
     unsigned long long point_passes;
     float warp_part[kWarps][16];   // per-warp sums of the pass accumulators (E, n, 11 moments or 6 gradient entries)
-    double hout[kWarps][21];       // per-warp sum of J J^T over the candidates that fell outside
+    double hout[kWarps][21];       // per-warp sum of J J^T over the candidates outside for sure, cumulative over a level's passes
+    double hout_pass[kWarps][21];  // per-warp sum of J J^T over this pass's deferred candidates that turned out outside
     double raw[kNumRaw];           // CTA / team totals of the raw accumulators
     double tot[32];                // finished pass: sum r^2, n_inside, g[6], H[21]
+#if VORS_TIMING
+    long long dbg[8][4];
+    long long dbgw[8][4];
+#endif
+    uint32_t near_words[kWarps][2 * 32];  // (word, mask) pairs flagged for deferred_pass by each warp in this pass
     alignas(8) unsigned long long full_bar[kWarps][kStages];
-    alignas(8) unsigned long long empty_bar[kWarps][kStages];
     alignas(128) float ring[kWarps][kStages * kStageWords];
-    // per-thread J J^T accumulators of the hot loop's outside candidates: 21 floats at a 28-word stride (16-byte
-    // vector accesses of a quarter warp then hit 8 distinct bank groups); zero between passes
+    // per-thread J J^T accumulators of the hot loop (candidates that changed sides of the frame border): 21 floats at a
+    // 28-word stride (16-byte vector accesses of a quarter warp then hit 8 distinct bank groups); zero between passes
     alignas(16) float hsm[kConsumers][kHsmStride];
 };
 
@@ -243,72 +272,112 @@ __shared__ LevelConst s_lc;
 // Deferred candidates.  The hot loop only evaluates candidates that are inside the frame for sure (fast warp, margin of
 // kBandPx); every other slot - padding, candidates near an inside-test boundary, candidates that fall outside - is
 // redirected to the zero page there (exact zero contributions) and flagged in a per-level bitmap in global memory
-// (one bit per candidate slot, laid out like the ring stages: word 4*stage + j, bit = lane, slot 2*lane + (j&1) + 64*(j>>1)).
+// (one bit per candidate slot: word = slot / 32, bit = slot % 32 = the lane that owned it).
 // After the hot loop each warp revisits the flagged slots of its own stages: the reference's own arithmetic
 // (lm_optimizer.rs:213-231) decides membership; inside candidates are evaluated in full, outside ones contribute
 // J J^T to H_outside.  Keeping all of this (and its function calls) out of the hot loop keeps that loop call-free.
+constexpr int kNearWords = 32;  // flagged bitmap words a warp remembers per pass (beyond that: full bitmap scan)
+
+// One deferred candidate: the reference's own warp decides (lm_optimizer.rs:213-231); inside -> full evaluation into
+// `acc`, outside -> J J^T into h.
 template <bool kSkew>
-__device__ __noinline__ void deferred_pass(int warp, int lane, int first_stage, int stage_stride, int n_stages, uint32_t* __restrict__ bitmap,
-                                           Acc* acc_io, int* n_fix) {
-    LmShared& S = lm_shared();
-    const LevelConst& lc = s_lc;
+__device__ __forceinline__ void eval_deferred(int i, const LevelConst& lc, const Pose& model, Acc& acc, int& fixed, float (&h)[21]) {
     const uint32_t* __restrict__ pts = lc.pts;
     const Intrinsics k = lc.k;
-    const uint8_t* __restrict__ img = lc.img;
     const int rows = int(lc.rows);
+    const uint32_t pk = __ldg(pts + pt_word(i, 0)), gr = __ldg(pts + pt_word(i, 2));
+    const float rho = __uint_as_float(__ldg(pts + pt_word(i, 1)));
+    const float x = float(rec_x(pk)), y = float(rec_y(pk));
+    const float gu = rec_gx(gr), gv = rec_gy(gr);
+    const float2 uv = warp_exact(model, k, x, y, rho);
+    // 0 <= floor(u) < W-2  <=>  0 <= u < W-2 (W-2 is an integer); NaN compares false -> outside
+    const bool inside = (uv.x >= 0.0f) && (uv.x < lc.wm2) && (uv.y >= 0.0f) && (uv.y < lc.hm2);
+    const float ca = x - lc.cx, cb = y - lc.cy;
+    if (inside) {
+        const float fu = floorf(uv.x), fv = floorf(uv.y);
+        const float a = uv.x - fu, b = uv.y - fv;
+        const uint8_t* p = lc.img + (size_t(int(fu)) * size_t(rows) + size_t(int(fv)));
+        const float t00 = float(__ldg(p)), t10 = float(__ldg(p + 1)), t01 = float(__ldg(p + rows)), t11 = float(__ldg(p + rows + 1));
+        const float val = (1.0f - b) * (1.0f - a) * t00 + b * (1.0f - a) * t10 + (1.0f - b) * a * t01 + b * a * t11;
+        const float r = val - float(rec_tmpl(pk));
+        acc.e = fmaf(r, r, acc.e);
+        ++fixed;
+        if (kSkew) {
+            float J[6];
+            jacobian_centred<true>(gu, gv, ca, cb, rho, k, J);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) acc.s[q] = fmaf(J[q], r, acc.s[q]);
+        } else {
+            accumulate_moments(acc, gu, gv, ca, cb, rho, r);
+        }
+    } else {
+        float J[6];
+        jacobian_centred<kSkew>(gu, gv, ca, cb, rho, k, J);
+#pragma unroll
+        for (int q = 0; q < 6; ++q)
+#pragma unroll
+            for (int d = q; d < 6; ++d) h[tri(q, d)] = fmaf(J[q], J[d], h[tri(q, d)]);
+    }
+}
+
+// `wlist`: the (word, mask) pairs this warp flagged in the hot loop (n_words of them, only the first kNearWords stored);
+// `scratch`: this warp's ring memory (idle between passes), used as the compacted candidate list.
+template <bool kSkew>
+__device__ __noinline__ void deferred_pass(int warp, int lane, int first_stage, int stage_stride, int n_stages, uint32_t* __restrict__ bitmap,
+                                           const uint32_t* wlist, int n_words, uint32_t* scratch, Acc* acc_io, int* n_fix) {
+    LmShared& S = lm_shared();
+    const LevelConst& lc = s_lc;
     Acc acc = *acc_io;
     int fixed = 0;
     float h[21];
 #pragma unroll
     for (int c = 0; c < 21; ++c) h[c] = 0.0f;
-    for (int c0 = first_stage; c0 < n_stages; c0 += 32 * stage_stride) {
-        const int c = c0 + lane * stage_stride;
-        if (c >= n_stages) continue;
-        uint4* wp = reinterpret_cast<uint4*>(bitmap) + c;
-        const uint4 w4 = *wp;
-        if ((w4.x | w4.y | w4.z | w4.w) == 0u) continue;
-        *wp = make_uint4(0u, 0u, 0u, 0u);
-        const uint32_t words[4] = {w4.x, w4.y, w4.z, w4.w};
+    if (n_words <= kNearWords) {
+        // common case: compact the flagged slots of the remembered words into a list, one candidate per lane and round
+        uint32_t word = 0u, mask = 0u;
+        if (lane < n_words) {
+            word = wlist[2 * lane];
+            mask = wlist[2 * lane + 1];
+            bitmap[word] = 0u;  // leave the bitmap all-zero for the next pass
+            const int base = int(word) * 32;
+            if (base + 32 > lc.n) mask = base >= lc.n ? 0u : (mask & ((1u << (lc.n - base)) - 1u));  // padding slots
+        }
+        const int cnt = __popc(mask);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int off = incl - cnt;
+        while (mask) {
+            scratch[off++] = word * 32u + uint32_t(__ffs(mask) - 1);
+            mask &= mask - 1u;
+        }
+        __syncwarp();
+        for (int e = lane; e < total; e += 32) eval_deferred<kSkew>(int(scratch[e]), lc, S.cand_model, acc, fixed, h);
+    } else {
+        // more flagged words than remembered: scan this warp's part of the bitmap, in groups of 128 slots (one uint4 of
+        // bitmap words), one group per lane and round
+        constexpr int kGroups = kStageCand / 128;
+        const int my_groups = first_stage < n_stages ? ((n_stages - first_stage + stage_stride - 1) / stage_stride) * kGroups : 0;
+        for (int g0 = 0; g0 < my_groups; g0 += 32) {
+            const int gi = g0 + lane;
+            if (gi >= my_groups) continue;
+            const int grp = (first_stage + (gi / kGroups) * stage_stride) * kGroups + gi % kGroups;  // 128-slot group index in the level
+            uint4* wp = reinterpret_cast<uint4*>(bitmap) + grp;
+            const uint4 w4 = *wp;
+            if ((w4.x | w4.y | w4.z | w4.w) == 0u) continue;
+            *wp = make_uint4(0u, 0u, 0u, 0u);
+            const uint32_t words[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-            uint32_t bits = words[j];
-            while (bits) {
-                const int l = __ffs(bits) - 1;
-                bits &= bits - 1u;
-                const int i = c * kStageCand + 2 * l + (j & 1) + kChunk * (j >> 1);
-                if (i >= lc.n) continue;  // padding
-                const uint32_t pk = __ldg(pts + pt_word(i, 0)), gr = __ldg(pts + pt_word(i, 2));
-                const float rho = __uint_as_float(__ldg(pts + pt_word(i, 1)));
-                const float x = float(rec_x(pk)), y = float(rec_y(pk));
-                const float gu = rec_gx(gr), gv = rec_gy(gr);
-                const float2 uv = warp_exact(S.cand_model, k, x, y, rho);
-                // 0 <= floor(u) < W-2  <=>  0 <= u < W-2 (W-2 is an integer); NaN compares false -> outside
-                const bool inside = (uv.x >= 0.0f) && (uv.x < lc.wm2) && (uv.y >= 0.0f) && (uv.y < lc.hm2);
-                const float ca = x - lc.cx, cb = y - lc.cy;
-                if (inside) {
-                    const float fu = floorf(uv.x), fv = floorf(uv.y);
-                    const float a = uv.x - fu, b = uv.y - fv;
-                    const uint8_t* p = img + (size_t(int(fu)) * size_t(rows) + size_t(int(fv)));
-                    const float t00 = float(__ldg(p)), t10 = float(__ldg(p + 1)), t01 = float(__ldg(p + rows)), t11 = float(__ldg(p + rows + 1));
-                    const float val = (1.0f - b) * (1.0f - a) * t00 + b * (1.0f - a) * t10 + (1.0f - b) * a * t01 + b * a * t11;
-                    const float r = val - float(rec_tmpl(pk));
-                    acc.e = fmaf(r, r, acc.e);
-                    ++fixed;
-                    if (kSkew) {
-                        float J[6];
-                        jacobian_centred<true>(gu, gv, ca, cb, rho, k, J);
-#pragma unroll
-                        for (int q = 0; q < 6; ++q) acc.s[q] = fmaf(J[q], r, acc.s[q]);
-                    } else {
-                        accumulate_moments(acc, gu, gv, ca, cb, rho, r);
-                    }
-                } else {
-                    float J[6];
-                    jacobian_centred<kSkew>(gu, gv, ca, cb, rho, k, J);
-#pragma unroll
-                    for (int q = 0; q < 6; ++q)
-#pragma unroll
-                        for (int d = q; d < 6; ++d) h[tri(q, d)] = fmaf(J[q], J[d], h[tri(q, d)]);
+            for (int j = 0; j < 4; ++j) {
+                uint32_t bits = words[j];
+                while (bits) {
+                    const int i = grp * 128 + 32 * j + __ffs(bits) - 1;
+                    bits &= bits - 1u;
+                    if (i < lc.n) eval_deferred<kSkew>(i, lc, S.cand_model, acc, fixed, h);  // else: padding
                 }
             }
         }
@@ -319,33 +388,37 @@ __device__ __noinline__ void deferred_pass(int warp, int lane, int first_stage, 
         float v = h[c];
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        if (lane == 0) S.hout[warp][c] += double(v);
+        if (lane == 0) S.hout_pass[warp][c] += double(v);
     }
     *acc_io = acc;
     *n_fix = fixed;
+    // `scratch` is ring memory: order these generic-proxy accesses before the next pass's bulk copies (async proxy)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 // Per-level constants the common path keeps in registers.
 struct PassConst {
     float cx, cy, su, sv, lim_lo, magic_u, magic_v, zero_u, zero_v;
     uint32_t rows;
+    uint32_t touch;
     const uint8_t* img_biased;
 };
 
 // Warp-uniform bookkeeping of the slots of a pass that the hot loop did not evaluate.
 struct Defer {
-    uint32_t* bitmap;  // this level's bitmap (global)
+    uint32_t* near;    // this level's bitmap of slots for deferred_pass (global; all zero between passes)
+    uint32_t* far;     // this level's bitmap of the slots that were outside for sure in the previous pass of the level
     int n_bad;         // slots of this pass redirected to the zero page so far
-    int any_far;       // some candidate of this warp went into hsm
+    int n_near;        // of which flagged in `near`
+    int n_words;       // bitmap words flagged in `near` during this pass
+    uint32_t* wlist;   // (word, mask) of the first kNearWords of them (shared memory)
+    int any_flip;      // this warp added to its hsm accumulators during this pass
+    int first_pass;    // first pass of the level: the far bitmap holds nothing yet
 };
 
-// J J^T of this lane's candidate (zero for lanes with `far` false) added to the thread's shared-memory accumulators.
+// +-J J^T of this lane's candidate (`sign` = +1 / -1 / 0) added to the thread's shared-memory accumulators.
 template <bool kSkew>
-__device__ __forceinline__ void add_outside(bool far, uint32_t gr, float a, float b, float rho, const Intrinsics& k, float* hs) {
-    float J[6];
-    jacobian_centred<kSkew>(rec_gx(gr), rec_gy(gr), a, b, rho, k, J);
-#pragma unroll
-    for (int c = 0; c < 6; ++c) J[c] = far ? J[c] : 0.0f;  // (padding slots carry a NaN inverse depth)
+__device__ __forceinline__ void add_outside(float sign, uint32_t gr, float a, float b, float rho, const Intrinsics& k, float* hs) {
     float4* h4 = reinterpret_cast<float4*>(hs);
     float h[24];
 #pragma unroll
@@ -353,20 +426,27 @@ __device__ __forceinline__ void add_outside(bool far, uint32_t gr, float a, floa
         const float4 t = h4[q];
         h[4 * q] = t.x; h[4 * q + 1] = t.y; h[4 * q + 2] = t.z; h[4 * q + 3] = t.w;
     }
+    float J[6];
+    // J is linear in the gradient: zero gradient (and a finite inverse depth: padding slots carry NaN) -> J = 0 exactly
+    const bool on = sign != 0.0f;
+    jacobian_centred<kSkew>(on ? rec_gx(gr) : 0.0f, on ? rec_gy(gr) : 0.0f, a, b, on ? rho : 0.0f, k, J);
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
+        const float jc = sign * J[c];
 #pragma unroll
-        for (int d = c; d < 6; ++d) h[tri(c, d)] = fmaf(J[c], J[d], h[tri(c, d)]);
+        for (int d = c; d < 6; ++d) h[tri(c, d)] = fmaf(jc, J[d], h[tri(c, d)]);
     }
 #pragma unroll
     for (int q = 0; q < 6; ++q) h4[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
 }
 
-// front: unpack, warp, inside test, texel gathers; branch-free unless some lane of the warp is not inside for sure.
-// `word` is the bitmap word of this call's 32 slots.
-template <bool kSkew>
-__device__ __forceinline__ void front(uint32_t pk, float rho, uint32_t gr, int word, const float (&M)[12], const PassConst& lc,
-                                      const Intrinsics& k, Defer& df, float* hs, int lane, Front& f) {
+// front, first half: unpack, warp, inside test - straight-line arithmetic that the compiler can interleave with the
+// `back` of the previous candidate (issued between the two halves).
+struct FrontA {
+    uint32_t pk, gr;
+    float rho, a, b, u, v, m;
+};
+__device__ __forceinline__ FrontA front_a(uint32_t pk, float rho, uint32_t gr, const float (&M)[12], const PassConst& lc) {
     // int -> float through the 2^23 magic number: one LOP3 (ALU pipe) + one FADD (FMA pipe) instead of mask + I2F
     const float x = __uint_as_float((pk & 0xFFFu) | 0x4B000000u) - 8388608.0f;
     const float y = float((pk >> 12) & 0xFFFu);
@@ -375,26 +455,62 @@ __device__ __forceinline__ void front(uint32_t pk, float rho, uint32_t gr, int w
     const float V = fmaf(M[4], a, fmaf(M[5], b, fmaf(M[7], rho, M[6])));
     const float W = fmaf(M[8], a, fmaf(M[9], b, fmaf(M[11], rho, M[10])));
     const float iw = rcp_approx(W);
-    float u = fmaf(U, iw, lc.cx), v = fmaf(V, iw, lc.cy);
+    FrontA o;
+    o.u = fmaf(U, iw, lc.cx);
+    o.v = fmaf(V, iw, lc.cy);
     // lm_optimizer.rs:231: inside iff 0 <= floor(u) < W-2 and 0 <= floor(v) < H-2; here: inside with a margin
-    const float m = fmaxf(fabsf(fmaf(u, lc.su, -1.0f)), fabsf(fmaf(v, lc.sv, -1.0f)));
-    const bool ok = m < lc.lim_lo;  // false for NaN
+    o.m = fmaxf(fabsf(fmaf(o.u, lc.su, -1.0f)), fabsf(fmaf(o.v, lc.sv, -1.0f)));
+    o.pk = pk;
+    o.gr = gr;
+    o.rho = rho;
+    o.a = a;
+    o.b = b;
+    return o;
+}
+
+// front, second half: the rare paths (warp-uniform branch), floor / fraction, texel gathers.
+// `word` is the bitmap word of this call's 32 slots.
+// `old_far`: the far-bitmap word of these 32 slots from the previous pass of the level.
+template <bool kSkew, bool kTouch>
+__device__ __forceinline__ void front_b(const FrontA& x, int word, unsigned old_far, const PassConst& lc, const Intrinsics& k, Defer& df,
+                                        float* hs, int lane, Front& f) {
+    uint32_t pk = x.pk;
+    float rho = x.rho, u = x.u, v = x.v;
+    const bool ok = x.m < lc.lim_lo;  // false for NaN
     const unsigned not_ok = __ballot_sync(0xffffffffu, !ok);
-    if (not_ok) {  // warp-uniform, rare
-        const bool far = m > s_lc.lim_hi;  // outside for sure (false for NaN): only J J^T is needed, formed here
-        const unsigned near = __ballot_sync(0xffffffffu, !ok && !far);
-        if (near && lane == 0) df.bitmap[word] = near;  // band / NaN / padding: see deferred_pass
-        df.n_bad += __popc(not_ok);
-        if (__any_sync(0xffffffffu, far)) {
-            add_outside<kSkew>(far, gr, a, b, rho, k, hs);
-            df.any_far = 1;
+    if (not_ok | old_far) {  // warp-uniform, rare
+        // H over the inside set = H_total - H_outside (lm_optimizer.rs:100 sums J J^T over the inside set).  H_outside is
+        // maintained incrementally across the passes of a level: only candidates that were outside for sure in the previous
+        // pass and are not now, or the reverse, add -+J J^T (after the first passes the pose barely moves: few flips).
+        const bool far = x.m > s_lc.lim_hi;  // outside for sure (false for NaN)
+        const unsigned far_mask = __ballot_sync(0xffffffffu, far), near_mask = not_ok & ~far_mask;
+        const unsigned flips = far_mask ^ old_far;
+        if (flips) {
+            const float sign = ((flips >> lane) & 1u) ? (far ? 1.0f : -1.0f) : 0.0f;
+            add_outside<kSkew>(sign, x.gr, x.a, x.b, rho, k, hs);
+            df.any_flip = 1;
         }
+        if (lane == 0) {
+            if (flips | unsigned(df.first_pass)) df.far[word] = far_mask;
+            if (near_mask) {  // band / NaN / padding: see deferred_pass
+                df.near[word] = near_mask;
+                if (df.n_words < kNearWords) {
+                    df.wlist[2 * df.n_words] = uint32_t(word);
+                    df.wlist[2 * df.n_words + 1] = near_mask;
+                }
+            }
+        }
+        df.n_words += near_mask ? 1 : 0;
+        df.n_bad += __popc(not_ok);
+        df.n_near += __popc(near_mask);
         if (!ok) {
             u = lc.zero_u;
             v = lc.zero_v;
             pk = 0u;   // template 0: r = 0 - 0
             rho = 0.0f;
         }
+    } else if (df.first_pass && lane == 0) {
+        df.far[word] = 0u;
     }
     // floor and fraction without F2I / I2F (see kMagicBits)
     const float tu = __fadd_rd(u, lc.magic_u), tv = __fadd_rd(v, lc.magic_v);
@@ -405,10 +521,19 @@ __device__ __forceinline__ void front(uint32_t pk, float rho, uint32_t gr, int w
     f.t10 = __ldg(p + 1);
     f.t01 = __ldg(p + lc.rows);
     f.t11 = __ldg(p + lc.rows + 1);
+#if VORS_TOUCH
+    // pull the image lines of this warp's next stage into L1 now (dense candidates in scan order: one team-stride of
+    // stages later = that many bytes further in the column-major image; harmless for sparse candidates)
+    if (kTouch) {
+        uint32_t d0, d1;
+        asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(d0) : "l"(p + lc.touch));
+        asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(d1) : "l"(p + lc.touch + lc.rows));
+    }
+#endif
     f.pk = pk;
-    f.gr = gr;
-    f.a = a;
-    f.b = b;
+    f.gr = x.gr;
+    f.a = x.a;
+    f.b = x.b;
     f.rho = rho;
 }
 
@@ -496,55 +621,84 @@ __device__ __noinline__ void lm_decide(LmShared& S, const AlignParams& P, const 
     }
     const Pose delta = se3_exp(b);
     S.cand_model = pose_renormalize(pose_mul(S.kept_model, pose_inverse(delta)));
-    warp_matrix(S.cand_model, job.lv[lvl].k, S.M, true);
-    S.cont = 1;
+    S.cont = 1;  // the caller publishes the candidate model's warp matrix
 }
 
-// Assemble sum r^2, n_inside, g[6], H[21] from the raw totals (one thread, f64).
+// Entry t of the finished pass (sum r^2, n_inside, g[6], H[21]) from the raw totals, f64; one lane of warp 0 per entry.
 template <bool kSkew>
-__device__ __forceinline__ void finish_pass(LmShared& S, const Intrinsics& k, const double* __restrict__ h_total) {
-    const double* raw = S.raw;
-    double* tot = S.tot;
-    tot[0] = raw[0];
-    tot[1] = raw[1];
-    if (kSkew) {
-        for (int c = 0; c < 6; ++c) tot[2 + c] = raw[2 + c];
-    } else {
-        const double* m = raw + 2;
-        const double fu = k.fx, fv = k.fy;
-        tot[2] = fu * m[kSrp];
-        tot[3] = fv * m[kSrq];
-        tot[4] = -m[kSrt];
-        tot[5] = -(m[kSabp] + m[kSbbq]) / fv - fv * m[kSq];
-        tot[6] = (m[kSaap] + m[kSabq]) / fu + fu * m[kSp];
-        tot[7] = (fv / fu) * m[kSaq] - (fu / fv) * m[kSbp];
+__device__ __forceinline__ double finish_entry(int t, const double* raw, const Intrinsics& k, const double* __restrict__ h_total) {
+    if (t < 2) return raw[t];
+    if (t >= 8) {
+        // H over the inside set = H_total (all candidates, per keyframe level) - H_outside; an empty inside set must give an
+        // exactly zero H (the reference then fails its Cholesky, lm_optimizer.rs:131-133)
+        return raw[1] > 0.0 ? h_total[t - 8] - raw[13 + (t - 8)] : 0.0;
     }
-    // H over the inside set = H_total (all candidates, per keyframe level) - H_outside; an empty inside set must give an
-    // exactly zero H (the reference then fails its Cholesky, lm_optimizer.rs:131-133)
-    for (int c = 0; c < 21; ++c) tot[8 + c] = raw[1] > 0.0 ? h_total[c] - raw[13 + c] : 0.0;
+    if (kSkew) return raw[t];
+    const double* m = raw + 2;
+    const double fu = k.fx, fv = k.fy;
+    switch (t) {
+        case 2: return fu * m[kSrp];
+        case 3: return fv * m[kSrq];
+        case 4: return -m[kSrt];
+        case 5: return -(m[kSabp] + m[kSbbq]) / fv - fv * m[kSq];
+        case 6: return (m[kSaap] + m[kSabq]) / fu + fu * m[kSp];
+        default: return (fv / fu) * m[kSaq] - (fu / fv) * m[kSbp];
+    }
+}
+
+// Entry e = 4 r + c of the centred warp matrix (lie.cuh `warp_matrix(..., centred = true)`), one lane of warp 0 per entry:
+// rows of P [R Ki | t] with P = [[fx, s, 0], [0, fy, 0], [0, 0, 1]], Ki = [[1/fx, -s/(fx fy), 0], [0, 1/fy, 0], [0, 0, 1]].
+__device__ __forceinline__ float warp_matrix_entry(int e, const Pose& m, const Intrinsics& k) {
+    const int r = e >> 2, c = e & 3;
+    const double qi = m.q.i, qj = m.q.j, qk = m.q.k, qw = m.q.w;
+    const double fx = k.fx, fy = k.fy, s = k.s;
+    // column c of A = [R Ki | t] (rotation matrix of the possibly slightly non-unit quaternion exactly as quat_rotate applies it)
+    double a0, a1, a2;
+    if (c == 3) {
+        a0 = m.t.x; a1 = m.t.y; a2 = m.t.z;
+    } else {
+        const double r00 = 1.0 - 2.0 * (qj * qj + qk * qk), r10 = 2.0 * (qi * qj + qk * qw), r20 = 2.0 * (qi * qk - qj * qw);
+        const double r01 = 2.0 * (qi * qj - qk * qw), r11 = 1.0 - 2.0 * (qi * qi + qk * qk), r21 = 2.0 * (qj * qk + qi * qw);
+        const double r02 = 2.0 * (qi * qk + qj * qw), r12 = 2.0 * (qj * qk - qi * qw), r22 = 1.0 - 2.0 * (qi * qi + qj * qj);
+        if (c == 0) {
+            const double ki = 1.0 / fx;
+            a0 = r00 * ki; a1 = r10 * ki; a2 = r20 * ki;
+        } else if (c == 1) {
+            const double k01 = -s / (fx * fy), k11 = 1.0 / fy;
+            a0 = r00 * k01 + r01 * k11; a1 = r10 * k01 + r11 * k11; a2 = r20 * k01 + r21 * k11;
+        } else {
+            a0 = r02; a1 = r12; a2 = r22;
+        }
+    }
+    return float(r == 0 ? fx * a0 + s * a1 : r == 1 ? fy * a1 : a2);
 }
 
 template <bool kSkew>
+#ifdef VORS_MAXREG
+__global__ void __maxnreg__(VORS_MAXREG) k_align(const AlignParams P) {
+#else
 __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignParams P) {
+#endif
     LmShared& S = lm_shared();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool is_producer = warp == kWarps;
     const int team = P.team;
     const int team_id = blockIdx.x / team, rank = blockIdx.x - team_id * team;
     const int n_teams = gridDim.x / team;
     TeamScratch* scratch = team > 1 ? P.scratch + team_id : nullptr;
     unsigned epoch = 0;      // passes this team has synchronised on so far (same in every CTA of the team)
-    uint32_t ring_count = 0; // stages this warp has consumed (consumer) / this lane has filled (producer lane w)
+    // this warp's TMA ring: slot of the next stage to consume and the parity its full barrier completes with
+    uint32_t ring_slot = 0, ring_parity = 0;
+    const uint32_t ring_base = smem_u32(&S.ring[warp][0]), bar_base = smem_u32(&S.full_bar[warp][0]);
     const uint64_t l2_policy = l2_evict_first_policy();
     if (tid == 0) {
         for (int w = 0; w < kWarps; ++w)
-            for (int st = 0; st < kStages; ++st) {
-                mbar_init(smem_u32(&S.full_bar[w][st]), 1);
-                mbar_init(smem_u32(&S.empty_bar[w][st]), 1);
-            }
+            for (int st = 0; st < kStages; ++st) mbar_init(smem_u32(&S.full_bar[w][st]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < kWarps * 21) (&S.hout[0][0])[tid] = 0.0;
+    if (tid < kWarps * 21) (&S.hout[0][0])[tid] = (&S.hout_pass[0][0])[tid] = 0.0;
+#if VORS_TIMING
+    if (tid < 64) (&S.dbg[0][0])[tid] = 0;
+#endif
     for (int i = tid; i < kConsumers * kHsmStride; i += kBlock) (&S.hsm[0][0])[i] = 0.0f;
     __syncthreads();
 
@@ -566,6 +720,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
             const uint32_t* __restrict__ pts = lj.pts;
             const int n_stages = (n + kStageCand - 1) / kStageCand;
             const int TW = team * kWarps;
+            if (tid < kWarps * 21) (&S.hout[0][0])[tid] = 0.0;
             if (tid == 0) {
                 const Intrinsics k = lj.k;
                 const int wm2i = lj.cols - 2, hm2i = lj.rows - 2;
@@ -589,35 +744,19 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                 c.k = k;
                 s_lc = c;
                 S.cand_model = S.out_model;
-                S.init_phase = 1;
-                warp_matrix(S.cand_model, k, S.M, true);
+                S.init_phase = 1;  // also: the level's far bitmap and H_outside start empty
+            }
+            if (warp == 0) {
+                __syncwarp();
+                if (lane < 12) S.M[lane] = warp_matrix_entry(lane, S.cand_model, s_lc.k);
             }
             __syncthreads();
 
             for (;;) {
-                if (is_producer) {
-                    // ---- producer warp: lane w feeds consumer warp w's ring (stages gw, gw + TW, ...) with one bulk copy
-                    // per stage; lanes poll their consumer's empty barrier without blocking each other
-                    int c = rank * kWarps + lane;
-                    bool active = lane < kWarps && c < n_stages;
-                    while (__any_sync(0xffffffffu, active)) {
-                        bool did = false;
-                        if (active) {
-                            const uint32_t stage = ring_count % kStages, use = ring_count / kStages;
-                            if (mbar_test(smem_u32(&S.empty_bar[lane][stage]), (use & 1u) ^ 1u)) {  // stage drained
-                                const uint32_t bar = smem_u32(&S.full_bar[lane][stage]);
-                                mbar_expect_tx(bar, kStageBytes);
-                                bulk_g2s(smem_u32(&S.ring[lane][stage * kStageWords]), pts + size_t(c) * kStageWords, kStageBytes, bar,
-                                         l2_policy);
-                                ++ring_count;
-                                c += TW;
-                                active = c < n_stages;
-                                did = true;
-                            }
-                        }
-                        if (!__any_sync(0xffffffffu, did)) __nanosleep(64);
-                    }
-                } else {
+#if VORS_TIMING
+                const long long t_pass0 = clock64();
+#endif
+                {
                     // ---- consumer warps: four candidates per lane per stage
                     float M[12];
 #pragma unroll
@@ -626,15 +765,21 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                     lc.cx = s_lc.cx; lc.cy = s_lc.cy; lc.su = s_lc.su; lc.sv = s_lc.sv; lc.lim_lo = s_lc.lim_lo;
                     lc.magic_u = s_lc.magic_u; lc.magic_v = s_lc.magic_v; lc.rows = s_lc.rows; lc.img_biased = s_lc.img_biased;
                     lc.zero_u = s_lc.zero_u; lc.zero_v = s_lc.zero_v;
+                    lc.touch = uint32_t(TW * kStageCand);
                     const Intrinsics k = s_lc.k;
                     Acc acc;
                     acc.e = 0.0f;
 #pragma unroll
                     for (int c = 0; c < 11; ++c) acc.s[c] = 0.0f;
                     Defer df;
-                    df.bitmap = lj.defer;
+                    df.near = lj.defer;
+                    df.far = lj.defer_far;
                     df.n_bad = 0;
-                    df.any_far = 0;
+                    df.n_near = 0;
+                    df.n_words = 0;
+                    df.wlist = S.near_words[warp];
+                    df.any_flip = 0;
+                    df.first_pass = S.init_phase;
                     float* hs = S.hsm[tid];
                     const int gw = rank * kWarps + warp;
                     int n_slots = 0;
@@ -643,37 +788,68 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                     Front fa, fb;
                     fb.pk = 0u; fb.gr = 0u; fb.a = 0.0f; fb.b = 0.0f; fb.rho = 0.0f; fb.fa = 0.0f; fb.fb = 0.0f;
                     fb.t00 = fb.t10 = fb.t01 = fb.t11 = 0u;
+                    // every warp streams its own stages (gw, gw + TW, ...) through its ring: lane 0 issues one bulk copy
+                    // per stage, kStages - 1 stages ahead of the one being consumed (SASS UBLKCP + SYNCS)
+                    if (lane == 0) {
+                        uint32_t slot = ring_slot;
+                        for (int j = 0, c = gw; j < kStages - 1 && c < n_stages; ++j, c += TW) {
+                            const uint32_t bar = bar_base + slot * 8u;
+                            mbar_expect_tx(bar, kStageBytes);
+                            bulk_g2s(ring_base + slot * kStageBytes, pts + size_t(c) * kStageWords, kStageBytes, bar, l2_policy);
+                            slot = (slot + 1 == kStages) ? 0u : slot + 1;
+                        }
+                    }
+                    // the stage's far-bitmap words of the previous pass (one per lane 0..kStageWordsBm-1), fetched one iteration ahead
+                    unsigned old_next = (lane < kStageWordsBm && !df.first_pass && gw < n_stages) ? __ldcg(df.far + kStageWordsBm * gw + lane) : 0u;
                     for (int c = gw; c < n_stages; c += TW) {
-                        const uint32_t stage = ring_count % kStages, use = ring_count / kStages;
-                        mbar_wait(smem_u32(&S.full_bar[warp][stage]), use & 1u);  // TMA bytes have landed
-                        const float* sp = &S.ring[warp][stage * kStageWords] + 2 * lane;
-                        // lane owns candidates 2*lane, 2*lane+1 of both chunks of the stage
-                        {
-                            const uint2 pk = *reinterpret_cast<const uint2*>(sp);
-                            const float2 rh = *reinterpret_cast<const float2*>(sp + kChunk);
-                            const uint2 gr = *reinterpret_cast<const uint2*>(sp + 2 * kChunk);
-                            front<kSkew>(pk.x, rh.x, gr.x, 4 * c, M, lc, k, df, hs, lane, fa);
-                            back<kSkew>(fb, k, acc);
-                            front<kSkew>(pk.y, rh.y, gr.y, 4 * c + 1, M, lc, k, df, hs, lane, fb);
-                            back<kSkew>(fa, k, acc);
+                        // refill the slot freed by the previous iteration (every lane consumed its loads before that
+                        // iteration's trailing __syncwarp) with the stage kStages - 1 ahead
+                        const int c_ahead = c + (kStages - 1) * TW;
+                        if (lane == 0 && c_ahead < n_stages) {
+                            const uint32_t slot = (ring_slot + kStages - 1 >= kStages) ? ring_slot - 1 : ring_slot + kStages - 1;
+                            const uint32_t bar = bar_base + slot * 8u;
+                            mbar_expect_tx(bar, kStageBytes);
+                            bulk_g2s(ring_base + slot * kStageBytes, pts + size_t(c_ahead) * kStageWords, kStageBytes, bar, l2_policy);
                         }
-                        {
-                            const uint2 pk = *reinterpret_cast<const uint2*>(sp + 3 * kChunk);
-                            const float2 rh = *reinterpret_cast<const float2*>(sp + 4 * kChunk);
-                            const uint2 gr = *reinterpret_cast<const uint2*>(sp + 5 * kChunk);
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(smem_u32(&S.empty_bar[warp][stage]));  // hand the stage back
-                            front<kSkew>(pk.x, rh.x, gr.x, 4 * c + 2, M, lc, k, df, hs, lane, fa);
-                            back<kSkew>(fb, k, acc);
-                            front<kSkew>(pk.y, rh.y, gr.y, 4 * c + 3, M, lc, k, df, hs, lane, fb);
-                            back<kSkew>(fa, k, acc);
+                        mbar_wait(bar_base + ring_slot * 8u, ring_parity);  // TMA bytes have landed
+                        const unsigned old_words = old_next;
+                        if (lane < kStageWordsBm && !df.first_pass && c + TW < n_stages) old_next = __ldcg(df.far + kStageWordsBm * (c + TW) + lane);
+                        const float* sp = &S.ring[warp][ring_slot * kStageWords] + lane;
+                        // word j of the stage = 32 consecutive candidates (chunk j / 2, half j % 2), one per lane
+#if VORS_PIPE == 1
+#define VORS_STEP(CH, HALF, FNEW, FOLD)                                                               \
+    {                                                                                                 \
+        const float* q = sp + (CH) * 3 * kChunk + (HALF) * 32;                                        \
+        const FrontA xa = front_a(__float_as_uint(q[0]), q[kChunk], __float_as_uint(q[2 * kChunk]), M, lc); \
+        back<kSkew>(FOLD, k, acc);                                                                    \
+        front_b<kSkew, false>(xa, kStageWordsBm * c + 2 * (CH) + (HALF), __shfl_sync(0xffffffffu, old_words, 2 * (CH) + (HALF)), lc, k, df, hs, lane, FNEW); \
+    }
+#else
+#define VORS_STEP(CH, HALF, FNEW, FOLD)                                                               \
+    {                                                                                                 \
+        const float* q = sp + (CH) * 3 * kChunk + (HALF) * 32;                                        \
+        const FrontA xa = front_a(__float_as_uint(q[0]), q[kChunk], __float_as_uint(q[2 * kChunk]), M, lc); \
+        front_b<kSkew, false>(xa, kStageWordsBm * c + 2 * (CH) + (HALF), __shfl_sync(0xffffffffu, old_words, 2 * (CH) + (HALF)), lc, k, df, hs, lane, FNEW); \
+        back<kSkew>(FOLD, k, acc);                                                                    \
+    }
+#endif
+#pragma unroll
+                        for (int ch = 0; ch < kStageChunks; ++ch) {
+                            VORS_STEP(ch, 0, fa, fb)
+                            VORS_STEP(ch, 1, fb, fa)
                         }
-                        ++ring_count;
+#undef VORS_STEP
+                        __syncwarp();  // all lanes are done with this slot: the next iteration may refill it
+                        ring_slot = (ring_slot + 1 == kStages) ? 0u : ring_slot + 1;
+                        ring_parity ^= (ring_slot == 0) ? 1u : 0u;
                         n_slots += kStageCand;
                     }
                     back<kSkew>(fb, k, acc);
+#if VORS_TIMING
+                    const long long t_hot = clock64();
+#endif
                     int n_bad = df.n_bad;
-                    if (df.any_far) {  // warp-uniform: fold this warp's per-thread J J^T sums into its f64 slot, re-zero them
+                    if (df.any_flip) {  // warp-uniform: fold this warp's per-thread +-J J^T sums into its f64 slot, re-zero them
 #pragma unroll
                         for (int c = 0; c < 21; ++c) {
                             float v = hs[c];
@@ -683,15 +859,25 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                             if (lane == 0) S.hout[warp][c] += double(v);
                         }
                     }
-                    if (n_bad > 0) {  // warp-uniform
+                    if (df.n_near > 0) {  // warp-uniform
                         int n_fix = 0;
                         Acc tmp = acc;  // only this copy has its address taken: `acc` itself stays in registers in the hot loop
-                        deferred_pass<kSkew>(warp, lane, gw, TW, n_stages, lj.defer, &tmp, &n_fix);
+                        deferred_pass<kSkew>(warp, lane, gw, TW, n_stages, lj.defer, df.wlist, df.n_words,
+                                             reinterpret_cast<uint32_t*>(&S.ring[warp][0]), &tmp, &n_fix);
                         acc = tmp;
 #pragma unroll
                         for (int d = 16; d > 0; d >>= 1) n_fix += __shfl_xor_sync(0xffffffffu, n_fix, d);
                         n_bad -= n_fix;
                     }
+#if VORS_TIMING
+                    const long long t_def = clock64();
+                    if (lane == 0 && lvl < 8) {
+                        atomicMax((unsigned long long*)&S.dbgw[lvl][0], (unsigned long long)(t_hot - t_pass0));
+                        atomicMax((unsigned long long*)&S.dbgw[lvl][1], (unsigned long long)(t_def - t_hot));
+                        atomicAdd((unsigned long long*)&S.dbgw[lvl][2], (unsigned long long)(t_def - t_hot));
+                        atomicAdd((unsigned long long*)&S.dbgw[lvl][3], (unsigned long long)(df.n_near));
+                    }
+#endif
                     // ---- reduce: warp shuffle, then per-CTA f64 sums in fixed order
                     float vals[13];
                     vals[0] = acc.e;
@@ -710,56 +896,75 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                         for (int c = 0; c < 13; ++c) S.warp_part[warp][c] = vals[c];
                     }
                 }
+#if VORS_TIMING
+                const long long t_pass1 = clock64();
+#endif
                 __syncthreads();
-                if (tid < kNumRaw) {
-                    double s = 0.0;
-                    if (tid < 13) {
+#if VORS_TIMING
+                const long long t_pass2 = clock64();
+#endif
+                // ---- reduce + finish + decide + step: warp 0 alone (redundantly identical in every CTA of a team), the other
+                // warps wait at the barrier below.  Per-CTA f64 sums in fixed order -> deterministic.
+                if (warp == 0) {
+                    for (int v = lane; v < kNumRaw; v += 32) {
+                        double s = 0.0;
+                        if (v < 13) {
 #pragma unroll
-                        for (int w = 0; w < kWarps; ++w) s += double(S.warp_part[w][tid]);
-                    } else {
+                            for (int w = 0; w < kWarps; ++w) s += double(S.warp_part[w][v]);
+                        } else {
 #pragma unroll
-                        for (int w = 0; w < kWarps; ++w) {
-                            s += S.hout[w][tid - 13];
-                            S.hout[w][tid - 13] = 0.0;
+                            for (int w = 0; w < kWarps; ++w) {
+                                s += S.hout[w][v - 13] + S.hout_pass[w][v - 13];  // hout: cumulative over the level's passes
+                                S.hout_pass[w][v - 13] = 0.0;
+                            }
+                        }
+                        if (team > 1)
+                            scratch->part[epoch & 1][rank][v] = s;
+                        else
+                            S.raw[v] = s;
+                    }
+                    if (team > 1) {  // peer partials through global memory, one counter barrier per pass
+                        __threadfence();
+                        __syncwarp();
+                        ++epoch;
+                        if (lane == 0) {
+                            atomicAdd(&scratch->counter, 1u);
+                            const unsigned target = epoch * unsigned(team);
+                            while (ld_acquire_u32(&scratch->counter) < target) __nanosleep(32);
+                        }
+                        __syncwarp();
+                        for (int v = lane; v < kNumRaw; v += 32) {
+                            double s = 0.0;
+                            const double* pp = &scratch->part[(epoch - 1) & 1][0][v];
+                            for (int r = 0; r < team; ++r) s += __ldcg(pp + r * 40);
+                            S.raw[v] = s;
                         }
                     }
-                    if (team > 1) {
-                        scratch->part[epoch & 1][rank][tid] = s;
-                        __threadfence();
-                    } else {
-                        S.raw[tid] = s;
+                    __syncwarp();
+                    if (lane < kNumAcc) S.tot[lane] = finish_entry<kSkew>(lane, S.raw, s_lc.k, lj.h_total);
+                    __syncwarp();
+                    if (lane == 0) {
+                        S.point_passes += (unsigned long long)n;
+                        if (job.pass_only) {
+                            S.n_passes += 1;
+                            S.cont = 0;
+                        } else {
+                            lm_decide(S, P, job, job_idx, lvl, writer);
+                        }
                     }
-                }
-                if (team > 1) {
-                    __syncthreads();
-                    ++epoch;
-                    if (tid == 0) {
-                        atomicAdd(&scratch->counter, 1u);
-                        const unsigned target = epoch * unsigned(team);
-                        while (ld_acquire_u32(&scratch->counter) < target) __nanosleep(32);
-                    }
-                    __syncthreads();
-                    if (tid < kNumRaw) {
-                        double s = 0.0;
-                        const double* pp = &scratch->part[(epoch - 1) & 1][0][tid];
-                        for (int r = 0; r < team; ++r) s += __ldcg(pp + r * 40);
-                        S.raw[tid] = s;
-                    }
+                    __syncwarp();
+                    if (S.cont && lane < 12) S.M[lane] = warp_matrix_entry(lane, S.cand_model, s_lc.k);
                 }
                 __syncthreads();
-
-                // ---- finish + decide + step (serial, redundantly identical in every CTA of the team)
-                if (tid == 0) {
-                    finish_pass<kSkew>(S, s_lc.k, lj.h_total);
-                    S.point_passes += (unsigned long long)n;
-                    if (job.pass_only) {
-                        S.n_passes += 1;
-                        S.cont = 0;
-                    } else {
-                        lm_decide(S, P, job, job_idx, lvl, writer);
-                    }
+#if VORS_TIMING
+                if (tid == 0 && lvl < 8) {
+                    const long long t_pass3 = clock64();
+                    S.dbg[lvl][0] += t_pass1 - t_pass0;  // warp 0: its share of the pass
+                    S.dbg[lvl][1] += t_pass2 - t_pass1;  // warp 0: waiting for the other warps
+                    S.dbg[lvl][2] += t_pass3 - t_pass2;  // reduction + serial finish / decide / step
+                    S.dbg[lvl][3] += 1;
                 }
-                __syncthreads();
+#endif
                 if (!S.cont) break;
             }
 
@@ -792,7 +997,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
             const int n = *lj.n_ptr;
             if (tid == 0) warp_matrix(S.out_model, lj.k, S.M);
             __syncthreads();
-            if (rank == 0 && !is_producer) {
+            if (rank == 0) {
                 float s = 0.0f;
                 for (int i = tid; i < n; i += kConsumers) {
                     const uint32_t p = lj.pts[pt_word(i, 0)];
@@ -814,6 +1019,15 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                 flow = float(t) / float(n);  // 0/0 = NaN with no candidates, like the reference
             }
         }
+#if VORS_TIMING
+        if (tid == 0 && (job_idx == 0 || job_idx == 147)) {
+            for (int l = 0; l < 8; ++l)
+                if (S.dbg[l][3])
+                    printf("job %d lvl %d passes %lld: pass %lld wait %lld serial %lld cycles/pass | max hot %lld max post %lld mean post %lld near/pass %lld\n", job_idx, l, S.dbg[l][3],
+                           S.dbg[l][0] / S.dbg[l][3], S.dbg[l][1] / S.dbg[l][3], S.dbg[l][2] / S.dbg[l][3], S.dbgw[l][0], S.dbgw[l][1], S.dbgw[l][2] / S.dbg[l][3] / kWarps, S.dbgw[l][3] / S.dbg[l][3]);
+        }
+        if (tid == 0) for (int l = 0; l < 8; ++l) S.dbg[l][0] = S.dbg[l][1] = S.dbg[l][2] = S.dbg[l][3] = S.dbgw[l][0] = S.dbgw[l][1] = S.dbgw[l][2] = S.dbgw[l][3] = 0;
+#endif
         if (writer && tid == 0) {
             AlignResult& R = P.results[job_idx];
             R.model = S.out_model;

@@ -112,7 +112,7 @@ class Engine {
     uint8_t* d_mask = nullptr;       // coarse-to-fine masks of all levels
     float* d_idepth = nullptr;       // idepth pyramid maps (NaN = unknown)
     float* d_weight = nullptr;
-    uint32_t* d_defer = nullptr;     // align kernel's deferred-slot bitmaps, pt_total / 32 words per stream
+    uint32_t* d_defer = nullptr;     // align kernel's deferred-slot bitmaps (near, far), 2 x pt_total / 32 words per stream
     uint32_t* d_pts = nullptr;       // chunk-blocked candidates, 3 * pt_total words per stream
     int* d_blk_count = nullptr;
     int* d_n_points = nullptr;       // [n][kMaxLevels]
@@ -225,8 +225,9 @@ class Engine {
         if (info.max_resident_ctas < 1) return fail(VORS_E_CUDA, "align kernel cannot be resident on this device");
 
         const size_t N = size_t(n), P = size_t(g.pix_stride), I = size_t(rows) * cols, PT = size_t(g.pt_total);
-        CU_TRY(cudaMalloc(&d_pyr, N * P));
-        CU_TRY(cudaMemsetAsync(d_pyr, 0, N * P, L.stream));  // the zero page of every slab stays zero: no kernel writes it
+        // + slack: the align kernel prefetches image lines up to one team-stride of stages past a texel
+        CU_TRY(cudaMalloc(&d_pyr, N * P + (size_t(1) << 20)));
+        CU_TRY(cudaMemsetAsync(d_pyr, 0, N * P + (size_t(1) << 20), L.stream));  // the zero page of every slab stays zero: no kernel writes it
         CU_TRY(cudaMalloc(&d_stage8, N * I));
         CU_TRY(cudaMalloc(&d_stage16, N * I * 2));
         CU_TRY(cudaMalloc(&d_depth, N * I * 2));
@@ -236,8 +237,8 @@ class Engine {
         CU_TRY(cudaMalloc(&d_idepth, N * P * 4));
         CU_TRY(cudaMalloc(&d_weight, N * P * 4));
         CU_TRY(cudaMalloc(&d_pts, N * PT * 12));
-        CU_TRY(cudaMalloc(&d_defer, N * PT / 8));
-        CU_TRY(cudaMemsetAsync(d_defer, 0, N * PT / 8, L.stream));  // the align kernel leaves it all-zero after every pass
+        CU_TRY(cudaMalloc(&d_defer, N * PT / 4));
+        CU_TRY(cudaMemsetAsync(d_defer, 0, N * PT / 4, L.stream));  // the align kernel leaves it all-zero after every pass
         // a partial last chunk is staged whole: keep its padding initialised
         CU_TRY(cudaMemsetAsync(d_pts, 0, N * PT * 12, L.stream));
         CU_TRY(cudaMalloc(&d_blk_count, N * size_t(g.blk_total) * 4));
@@ -280,6 +281,7 @@ class Engine {
             LevelJob& lj = j.lv[l];
             lj.pts = d_pts + 3 * (pbase + g.pt_off[l]);
             lj.defer = d_defer + (pbase + g.pt_off[l]) / 32;
+            lj.defer_far = d_defer + (size_t(n) * g.pt_total + pbase + g.pt_off[l]) / 32;
             lj.img = d_pyr + base + g.off[l];
             lj.n_ptr = d_n_points + stream * kMaxLevels + l;
             lj.h_total = d_h_total + (size_t(stream) * kMaxLevels + l) * kHStride;

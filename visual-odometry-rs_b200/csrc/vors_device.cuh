@@ -28,7 +28,10 @@ constexpr int kCompactBlock = 1024;  // elements per ordered-compaction block
 constexpr int kTraceCap = 256;       // trace records kept per alignment
 constexpr int kMaxTeam = 160;        // CTAs cooperating on one alignment (<= one per SM)
 constexpr int kChunk = 64;          // candidates per chunk-blocked record (768 B)
-constexpr int kPtAlign = 128;        // a level's candidate block is padded to this many candidates (one align-kernel ring stage)
+#ifndef VORS_STAGE_CHUNKS
+#define VORS_STAGE_CHUNKS 4
+#endif
+constexpr int kPtAlign = VORS_STAGE_CHUNKS * kChunk;  // a level's candidate block is padded to this many candidates (one align-kernel ring stage)
 constexpr int kHStride = 24;         // doubles per (stream, level) in the H_total table (21 used)
 constexpr int kNumAcc = 29;          // finished pass: sum r^2, n_inside, g[6], H[21] (upper triangle)
 constexpr int kNumRaw = 34;          // raw pass accumulators: sum r^2, n_inside, 11 gradient moments (or g[6]), H_outside[21]
@@ -68,6 +71,7 @@ struct LevelJob {
     const int* n_ptr;    // number of candidates (device memory: written by the compaction kernels)
     const double* h_total;  // sum over ALL candidates of J J^T, 21 upper-triangle entries (k_h_total)
     uint32_t* defer;     // bitmap of the level's candidate slots the align kernel's hot loop deferred (all zero between passes)
+    uint32_t* defer_far; // same, for the slots it found outside for sure
     int rows, cols;
     float zero_u, zero_v;  // integer-valued image coordinates whose 2x2 footprint is the slab's zero page
     Intrinsics k;
