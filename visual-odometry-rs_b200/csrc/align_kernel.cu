@@ -60,6 +60,7 @@ namespace {
 constexpr int kWarps = VORS_WARPS;            // warps per CTA; every warp refills its own TMA ring
 constexpr int kConsumers = kWarps * 32;
 constexpr int kBlock = kConsumers;
+constexpr int kSerialWarp = kWarps - 1;       // runs the serial part of every LM round
 constexpr int kMinCtasPerSm = VORS_MIN_CTAS;  // 10 warps x 2 CTAs: register cap 96, 20 warps per SM
 constexpr int kStageChunks = VORS_STAGE_CHUNKS;  // chunk-blocked records per ring stage
 constexpr int kStageCand = kStageChunks * kChunk;  // candidates per stage, 2 per lane per chunk (== kPtAlign)
@@ -240,6 +241,7 @@ struct LevelConst {
     const uint8_t* img;
     const uint32_t* pts;        // the level's chunk-blocked candidates (deferred pass)
     Intrinsics k;
+    double inv_fx, inv_fy, k01;  // 1/fx, 1/fy, -s/(fx fy): the f64 divisions of the per-pass serial part, done once per level
 };
 
 // Chooses Cu so that (bits(Cu) * rows + bits(Cv)) mod 2^32 plus any texel offset of the slab (< 2^27) cannot wrap.
@@ -470,15 +472,17 @@ __device__ __forceinline__ FrontA front_a(uint32_t pk, float rho, uint32_t gr, c
 
 // front, second half: the rare paths (warp-uniform branch), floor / fraction, texel gathers.
 // `word` is the bitmap word of this call's 32 slots.
-// `old_far`: the far-bitmap word of these 32 slots from the previous pass of the level.
+// `old_words`: lane j holds the far-bitmap word of the stage's word j from the previous pass of the level; bit j of
+// `old_nz` says whether it is non-zero.  `j` = this call's word within the stage.
 template <bool kSkew, bool kTouch>
-__device__ __forceinline__ void front_b(const FrontA& x, int word, unsigned old_far, const PassConst& lc, const Intrinsics& k, Defer& df,
-                                        float* hs, int lane, Front& f) {
+__device__ __forceinline__ void front_b(const FrontA& x, int word, int j, unsigned old_words, unsigned old_nz, const PassConst& lc,
+                                        const Intrinsics& k, Defer& df, float* hs, int lane, Front& f) {
     uint32_t pk = x.pk;
     float rho = x.rho, u = x.u, v = x.v;
     const bool ok = x.m < lc.lim_lo;  // false for NaN
     const unsigned not_ok = __ballot_sync(0xffffffffu, !ok);
-    if (not_ok | old_far) {  // warp-uniform, rare
+    if (not_ok | ((old_nz >> j) & 1u)) {  // warp-uniform, rare
+        const unsigned old_far = __shfl_sync(0xffffffffu, old_words, j);
         // H over the inside set = H_total - H_outside (lm_optimizer.rs:100 sums J J^T over the inside set).  H_outside is
         // maintained incrementally across the passes of a level: only candidates that were outside for sure in the previous
         // pass and are not now, or the reverse, add -+J J^T (after the first passes the pose barely moves: few flips).
@@ -491,7 +495,7 @@ __device__ __forceinline__ void front_b(const FrontA& x, int word, unsigned old_
             df.any_flip = 1;
         }
         if (lane == 0) {
-            if (flips | unsigned(df.first_pass)) df.far[word] = far_mask;
+            if (flips) df.far[word] = far_mask;
             if (near_mask) {  // band / NaN / padding: see deferred_pass
                 df.near[word] = near_mask;
                 if (df.n_words < kNearWords) {
@@ -509,8 +513,6 @@ __device__ __forceinline__ void front_b(const FrontA& x, int word, unsigned old_
             pk = 0u;   // template 0: r = 0 - 0
             rho = 0.0f;
         }
-    } else if (df.first_pass && lane == 0) {
-        df.far[word] = 0u;
     }
     // floor and fraction without F2I / I2F (see kMagicBits)
     const float tu = __fadd_rd(u, lc.magic_u), tv = __fadd_rd(v, lc.magic_v);
@@ -626,7 +628,7 @@ __device__ __noinline__ void lm_decide(LmShared& S, const AlignParams& P, const 
 
 // Entry t of the finished pass (sum r^2, n_inside, g[6], H[21]) from the raw totals, f64; one lane of warp 0 per entry.
 template <bool kSkew>
-__device__ __forceinline__ double finish_entry(int t, const double* raw, const Intrinsics& k, const double* __restrict__ h_total) {
+__device__ __forceinline__ double finish_entry(int t, const double* raw, const LevelConst& lc, const double* __restrict__ h_total) {
     if (t < 2) return raw[t];
     if (t >= 8) {
         // H over the inside set = H_total (all candidates, per keyframe level) - H_outside; an empty inside set must give an
@@ -635,23 +637,23 @@ __device__ __forceinline__ double finish_entry(int t, const double* raw, const I
     }
     if (kSkew) return raw[t];
     const double* m = raw + 2;
-    const double fu = k.fx, fv = k.fy;
+    const double fu = lc.k.fx, fv = lc.k.fy;
     switch (t) {
         case 2: return fu * m[kSrp];
         case 3: return fv * m[kSrq];
         case 4: return -m[kSrt];
-        case 5: return -(m[kSabp] + m[kSbbq]) / fv - fv * m[kSq];
-        case 6: return (m[kSaap] + m[kSabq]) / fu + fu * m[kSp];
-        default: return (fv / fu) * m[kSaq] - (fu / fv) * m[kSbp];
+        case 5: return -(m[kSabp] + m[kSbbq]) * lc.inv_fy - fv * m[kSq];
+        case 6: return (m[kSaap] + m[kSabq]) * lc.inv_fx + fu * m[kSp];
+        default: return (fv * lc.inv_fx) * m[kSaq] - (fu * lc.inv_fy) * m[kSbp];
     }
 }
 
 // Entry e = 4 r + c of the centred warp matrix (lie.cuh `warp_matrix(..., centred = true)`), one lane of warp 0 per entry:
 // rows of P [R Ki | t] with P = [[fx, s, 0], [0, fy, 0], [0, 0, 1]], Ki = [[1/fx, -s/(fx fy), 0], [0, 1/fy, 0], [0, 0, 1]].
-__device__ __forceinline__ float warp_matrix_entry(int e, const Pose& m, const Intrinsics& k) {
+__device__ __forceinline__ float warp_matrix_entry(int e, const Pose& m, const LevelConst& lc) {
     const int r = e >> 2, c = e & 3;
     const double qi = m.q.i, qj = m.q.j, qk = m.q.k, qw = m.q.w;
-    const double fx = k.fx, fy = k.fy, s = k.s;
+    const double fx = lc.k.fx, fy = lc.k.fy, s = lc.k.s;
     // column c of A = [R Ki | t] (rotation matrix of the possibly slightly non-unit quaternion exactly as quat_rotate applies it)
     double a0, a1, a2;
     if (c == 3) {
@@ -661,10 +663,10 @@ __device__ __forceinline__ float warp_matrix_entry(int e, const Pose& m, const I
         const double r01 = 2.0 * (qi * qj - qk * qw), r11 = 1.0 - 2.0 * (qi * qi + qk * qk), r21 = 2.0 * (qj * qk + qi * qw);
         const double r02 = 2.0 * (qi * qk + qj * qw), r12 = 2.0 * (qj * qk - qi * qw), r22 = 1.0 - 2.0 * (qi * qi + qj * qj);
         if (c == 0) {
-            const double ki = 1.0 / fx;
+            const double ki = lc.inv_fx;
             a0 = r00 * ki; a1 = r10 * ki; a2 = r20 * ki;
         } else if (c == 1) {
-            const double k01 = -s / (fx * fy), k11 = 1.0 / fy;
+            const double k01 = lc.k01, k11 = lc.inv_fy;
             a0 = r00 * k01 + r01 * k11; a1 = r10 * k01 + r11 * k11; a2 = r20 * k01 + r21 * k11;
         } else {
             a0 = r02; a1 = r12; a2 = r22;
@@ -742,13 +744,16 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                 c.img = lj.img;
                 c.pts = pts;
                 c.k = k;
+                c.inv_fx = 1.0 / double(k.fx);
+                c.inv_fy = 1.0 / double(k.fy);
+                c.k01 = -double(k.s) / (double(k.fx) * double(k.fy));
                 s_lc = c;
                 S.cand_model = S.out_model;
                 S.init_phase = 1;  // also: the level's far bitmap and H_outside start empty
             }
             if (warp == 0) {
                 __syncwarp();
-                if (lane < 12) S.M[lane] = warp_matrix_entry(lane, S.cand_model, s_lc.k);
+                if (lane < 12) S.M[lane] = warp_matrix_entry(lane, S.cand_model, s_lc);
             }
             __syncthreads();
 
@@ -799,6 +804,11 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                             slot = (slot + 1 == kStages) ? 0u : slot + 1;
                         }
                     }
+                    if (df.first_pass) {  // the level's far bitmap starts empty: clear the words of this warp's stages
+                        for (int c = gw; c < n_stages; c += TW)
+                            if (lane < kStageWordsBm) df.far[kStageWordsBm * c + lane] = 0u;
+                        __syncwarp();  // orders these stores before lane 0's later stores to the same words
+                    }
                     // the stage's far-bitmap words of the previous pass (one per lane 0..kStageWordsBm-1), fetched one iteration ahead
                     unsigned old_next = (lane < kStageWordsBm && !df.first_pass && gw < n_stages) ? __ldcg(df.far + kStageWordsBm * gw + lane) : 0u;
                     for (int c = gw; c < n_stages; c += TW) {
@@ -813,6 +823,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                         }
                         mbar_wait(bar_base + ring_slot * 8u, ring_parity);  // TMA bytes have landed
                         const unsigned old_words = old_next;
+                        const unsigned old_nz = __ballot_sync(0xffffffffu, old_words != 0u);
                         if (lane < kStageWordsBm && !df.first_pass && c + TW < n_stages) old_next = __ldcg(df.far + kStageWordsBm * (c + TW) + lane);
                         const float* sp = &S.ring[warp][ring_slot * kStageWords] + lane;
                         // word j of the stage = 32 consecutive candidates (chunk j / 2, half j % 2), one per lane
@@ -822,14 +833,14 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
         const float* q = sp + (CH) * 3 * kChunk + (HALF) * 32;                                        \
         const FrontA xa = front_a(__float_as_uint(q[0]), q[kChunk], __float_as_uint(q[2 * kChunk]), M, lc); \
         back<kSkew>(FOLD, k, acc);                                                                    \
-        front_b<kSkew, false>(xa, kStageWordsBm * c + 2 * (CH) + (HALF), __shfl_sync(0xffffffffu, old_words, 2 * (CH) + (HALF)), lc, k, df, hs, lane, FNEW); \
+        front_b<kSkew, false>(xa, kStageWordsBm * c + 2 * (CH) + (HALF), 2 * (CH) + (HALF), old_words, old_nz, lc, k, df, hs, lane, FNEW); \
     }
 #else
 #define VORS_STEP(CH, HALF, FNEW, FOLD)                                                               \
     {                                                                                                 \
         const float* q = sp + (CH) * 3 * kChunk + (HALF) * 32;                                        \
         const FrontA xa = front_a(__float_as_uint(q[0]), q[kChunk], __float_as_uint(q[2 * kChunk]), M, lc); \
-        front_b<kSkew, false>(xa, kStageWordsBm * c + 2 * (CH) + (HALF), __shfl_sync(0xffffffffu, old_words, 2 * (CH) + (HALF)), lc, k, df, hs, lane, FNEW); \
+        front_b<kSkew, false>(xa, kStageWordsBm * c + 2 * (CH) + (HALF), 2 * (CH) + (HALF), old_words, old_nz, lc, k, df, hs, lane, FNEW); \
         back<kSkew>(FOLD, k, acc);                                                                    \
     }
 #endif
@@ -903,9 +914,10 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
 #if VORS_TIMING
                 const long long t_pass2 = clock64();
 #endif
-                // ---- reduce + finish + decide + step: warp 0 alone (redundantly identical in every CTA of a team), the other
-                // warps wait at the barrier below.  Per-CTA f64 sums in fixed order -> deterministic.
-                if (warp == 0) {
+                // ---- reduce + finish + decide + step: one warp alone (redundantly identical in every CTA of a team), the
+                // other warps wait at the barrier below.  The last warp: the scheduler favours higher warp ids, so the serial
+                // chain is not starved by the co-resident CTA's hot loop.  Per-CTA f64 sums in fixed order -> deterministic.
+                if (warp == kSerialWarp) {
                     for (int v = lane; v < kNumRaw; v += 32) {
                         double s = 0.0;
                         if (v < 13) {
@@ -941,7 +953,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                         }
                     }
                     __syncwarp();
-                    if (lane < kNumAcc) S.tot[lane] = finish_entry<kSkew>(lane, S.raw, s_lc.k, lj.h_total);
+                    if (lane < kNumAcc) S.tot[lane] = finish_entry<kSkew>(lane, S.raw, s_lc, lj.h_total);
                     __syncwarp();
                     if (lane == 0) {
                         S.point_passes += (unsigned long long)n;
@@ -953,7 +965,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                         }
                     }
                     __syncwarp();
-                    if (S.cont && lane < 12) S.M[lane] = warp_matrix_entry(lane, S.cand_model, s_lc.k);
+                    if (S.cont && lane < 12) S.M[lane] = warp_matrix_entry(lane, S.cand_model, s_lc);
                 }
                 __syncthreads();
 #if VORS_TIMING
