@@ -91,11 +91,13 @@ struct LmShared {
     float warp_part[kWarps][16];   // per-warp sums of the pass accumulators (E, n, 11 moments or 6 gradient entries)
     double hout[kWarps][21];       // per-warp sum of J J^T over the candidates outside for sure, cumulative over a level's passes
     double hout_pass[kWarps][21];  // per-warp sum of J J^T over this pass's deferred candidates that turned out outside
+    double h_total[21];            // the level's H_total (k_h_total), cached for the per-pass serial part
     double raw[kNumRaw];           // CTA / team totals of the raw accumulators
     double tot[32];                // finished pass: sum r^2, n_inside, g[6], H[21]
 #if VORS_TIMING
     long long dbg[8][4];
     long long dbgw[8][4];
+    long long dbgs[8][4];
 #endif
     uint32_t near_words[kWarps][2 * 32];  // (word, mask) pairs flagged for deferred_pass by each warp in this pass
     alignas(8) unsigned long long full_bar[kWarps][kStages];
@@ -487,7 +489,10 @@ __device__ __forceinline__ void front_b(const FrontA& x, int word, int j, unsign
         // maintained incrementally across the passes of a level: only candidates that were outside for sure in the previous
         // pass and are not now, or the reverse, add -+J J^T (after the first passes the pose barely moves: few flips).
         const bool far = x.m > s_lc.lim_hi;  // outside for sure (false for NaN)
-        const unsigned far_mask = __ballot_sync(0xffffffffu, far), near_mask = not_ok & ~far_mask;
+        // padding slots (NaN inverse depth: never `far`) need no second look
+        const int n_live = s_lc.n - 32 * word;
+        const unsigned live_mask = n_live >= 32 ? 0xffffffffu : n_live <= 0 ? 0u : (1u << n_live) - 1u;
+        const unsigned far_mask = __ballot_sync(0xffffffffu, far), near_mask = not_ok & ~far_mask & live_mask;
         const unsigned flips = far_mask ^ old_far;
         if (flips) {
             const float sign = ((flips >> lane) & 1u) ? (far ? 1.0f : -1.0f) : 0.0f;
@@ -601,7 +606,9 @@ __device__ __noinline__ void lm_decide(LmShared& S, const AlignParams& P, const 
     S.trace_len += 1;
     if (accepted) {
         S.keptE = E;
+#pragma unroll
         for (int c = 0; c < 6; ++c) S.keptg[c] = float(tot[2 + c]);
+#pragma unroll
         for (int c = 0; c < 21; ++c) S.keptH[c] = float(tot[8 + c]);
         S.kept_model = S.cand_model;
     }
@@ -612,9 +619,13 @@ __device__ __noinline__ void lm_decide(LmShared& S, const AlignParams& P, const 
     // step (lm_optimizer.rs:123-136)
     S.iter += 1;
     float A[36], b[6];
+#pragma unroll
     for (int r = 0; r < 6; ++r)
+#pragma unroll
         for (int c = 0; c < 6; ++c) A[r * 6 + c] = S.keptH[r <= c ? tri(r, c) : tri(c, r)];
+#pragma unroll
     for (int c = 0; c < 6; ++c) A[c * 6 + c] *= 1.0f + S.lam;
+#pragma unroll
     for (int c = 0; c < 6; ++c) b[c] = S.keptg[c];
     if (!cholesky6_solve(A, b)) {
         S.failed = 1;
@@ -628,7 +639,7 @@ __device__ __noinline__ void lm_decide(LmShared& S, const AlignParams& P, const 
 
 // Entry t of the finished pass (sum r^2, n_inside, g[6], H[21]) from the raw totals, f64; one lane of warp 0 per entry.
 template <bool kSkew>
-__device__ __forceinline__ double finish_entry(int t, const double* raw, const LevelConst& lc, const double* __restrict__ h_total) {
+__device__ __forceinline__ double finish_entry(int t, const double* raw, const LevelConst& lc, const double* h_total) {
     if (t < 2) return raw[t];
     if (t >= 8) {
         // H over the inside set = H_total (all candidates, per keyframe level) - H_outside; an empty inside set must give an
@@ -699,7 +710,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
     }
     if (tid < kWarps * 21) (&S.hout[0][0])[tid] = (&S.hout_pass[0][0])[tid] = 0.0;
 #if VORS_TIMING
-    if (tid < 64) (&S.dbg[0][0])[tid] = 0;
+    if (tid < 96) (&S.dbg[0][0])[tid] = 0;
 #endif
     for (int i = tid; i < kConsumers * kHsmStride; i += kBlock) (&S.hsm[0][0])[i] = 0.0f;
     __syncthreads();
@@ -723,6 +734,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
             const int n_stages = (n + kStageCand - 1) / kStageCand;
             const int TW = team * kWarps;
             if (tid < kWarps * 21) (&S.hout[0][0])[tid] = 0.0;
+            if (tid >= 32 && tid < 32 + 21) S.h_total[tid - 32] = lj.h_total[tid - 32];
             if (tid == 0) {
                 const Intrinsics k = lj.k;
                 const int wm2i = lj.cols - 2, hm2i = lj.rows - 2;
@@ -918,6 +930,9 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                 // other warps wait at the barrier below.  The last warp: the scheduler favours higher warp ids, so the serial
                 // chain is not starved by the co-resident CTA's hot loop.  Per-CTA f64 sums in fixed order -> deterministic.
                 if (warp == kSerialWarp) {
+#if VORS_TIMING
+                    const long long ts0 = clock64();
+#endif
                     for (int v = lane; v < kNumRaw; v += 32) {
                         double s = 0.0;
                         if (v < 13) {
@@ -953,8 +968,14 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                         }
                     }
                     __syncwarp();
-                    if (lane < kNumAcc) S.tot[lane] = finish_entry<kSkew>(lane, S.raw, s_lc, lj.h_total);
+#if VORS_TIMING
+                    const long long ts1 = clock64();
+#endif
+                    if (lane < kNumAcc) S.tot[lane] = finish_entry<kSkew>(lane, S.raw, s_lc, S.h_total);
                     __syncwarp();
+#if VORS_TIMING
+                    const long long ts2 = clock64();
+#endif
                     if (lane == 0) {
                         S.point_passes += (unsigned long long)n;
                         if (job.pass_only) {
@@ -965,7 +986,17 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                         }
                     }
                     __syncwarp();
+#if VORS_TIMING
+                    const long long ts3 = clock64();
+#endif
                     if (S.cont && lane < 12) S.M[lane] = warp_matrix_entry(lane, S.cand_model, s_lc);
+#if VORS_TIMING
+                    __syncwarp();
+                    if (lane == 0 && lvl < 8) {
+                        const long long ts4 = clock64();
+                        S.dbgs[lvl][0] += ts1 - ts0; S.dbgs[lvl][1] += ts2 - ts1; S.dbgs[lvl][2] += ts3 - ts2; S.dbgs[lvl][3] += ts4 - ts3;
+                    }
+#endif
                 }
                 __syncthreads();
 #if VORS_TIMING
@@ -1035,10 +1066,11 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
         if (tid == 0 && (job_idx == 0 || job_idx == 147)) {
             for (int l = 0; l < 8; ++l)
                 if (S.dbg[l][3])
-                    printf("job %d lvl %d passes %lld: pass %lld wait %lld serial %lld cycles/pass | max hot %lld max post %lld mean post %lld near/pass %lld\n", job_idx, l, S.dbg[l][3],
-                           S.dbg[l][0] / S.dbg[l][3], S.dbg[l][1] / S.dbg[l][3], S.dbg[l][2] / S.dbg[l][3], S.dbgw[l][0], S.dbgw[l][1], S.dbgw[l][2] / S.dbg[l][3] / kWarps, S.dbgw[l][3] / S.dbg[l][3]);
+                    printf("job %d lvl %d passes %lld: pass %lld wait %lld serial %lld cycles/pass | max hot %lld max post %lld mean post %lld near/pass %lld | reduce %lld finish %lld decide %lld M %lld\n", job_idx, l, S.dbg[l][3],
+                           S.dbg[l][0] / S.dbg[l][3], S.dbg[l][1] / S.dbg[l][3], S.dbg[l][2] / S.dbg[l][3], S.dbgw[l][0], S.dbgw[l][1], S.dbgw[l][2] / S.dbg[l][3] / kWarps, S.dbgw[l][3] / S.dbg[l][3],
+                           S.dbgs[l][0] / S.dbg[l][3], S.dbgs[l][1] / S.dbg[l][3], S.dbgs[l][2] / S.dbg[l][3], S.dbgs[l][3] / S.dbg[l][3]);
         }
-        if (tid == 0) for (int l = 0; l < 8; ++l) S.dbg[l][0] = S.dbg[l][1] = S.dbg[l][2] = S.dbg[l][3] = S.dbgw[l][0] = S.dbgw[l][1] = S.dbgw[l][2] = S.dbgw[l][3] = 0;
+        if (tid == 0) for (int l = 0; l < 8; ++l) S.dbg[l][0] = S.dbg[l][1] = S.dbg[l][2] = S.dbg[l][3] = S.dbgw[l][0] = S.dbgw[l][1] = S.dbgw[l][2] = S.dbgw[l][3] = S.dbgs[l][0] = S.dbgs[l][1] = S.dbgs[l][2] = S.dbgs[l][3] = 0;
 #endif
         if (writer && tid == 0) {
             AlignResult& R = P.results[job_idx];

@@ -186,24 +186,33 @@ VORS_HD void se3_log(const Pose& iso, float xi[6]) {
 // transposed-back substitution.  A is row-major 6x6 (only the lower triangle is read), b is
 // overwritten with the solution.  Returns false when the decomposition fails.
 VORS_HD bool cholesky6_solve(float A[36], float b[6]) {
+    // fully unrolled: on the device A and b then live in registers (the LM step is a latency-bound single-thread chain)
+#pragma unroll
     for (int j = 0; j < 6; ++j) {
+#pragma unroll
         for (int k = 0; k < j; ++k) {
             const float factor = -A[j * 6 + k];
+#pragma unroll
             for (int i = j; i < 6; ++i) A[i * 6 + j] = factor * A[i * 6 + k] + A[i * 6 + j];
         }
         const float diag = A[j * 6 + j];
         if (!(diag > 0.0f)) return false;
         const float denom = sqrtf(diag);
         A[j * 6 + j] = denom;
+#pragma unroll
         for (int i = j + 1; i < 6; ++i) A[i * 6 + j] /= denom;
     }
+#pragma unroll
     for (int i = 0; i < 6; ++i) {
         const float coeff = b[i] / A[i * 6 + i];
         b[i] = coeff;
+#pragma unroll
         for (int r = i + 1; r < 6; ++r) b[r] = (-coeff) * A[r * 6 + i] + b[r];
     }
+#pragma unroll
     for (int i = 5; i >= 0; --i) {
         float dot = 0.0f;
+#pragma unroll
         for (int r = i + 1; r < 6; ++r) dot += A[r * 6 + i] * b[r];
         b[i] = (b[i] - dot) / A[i * 6 + i];
     }
