@@ -240,14 +240,18 @@ def run_ours(args):
     bt = new_tracker()
     img_ptrs = [ptr_array(gray_h[k].data_ptr(), B, I) for k in range(T + 1)]
     dep_ptrs = [ptr_array(depth_h[k].data_ptr(), B, I * 2) for k in range(T + 1)]
+    # every call announces the next step's host frames (a streaming caller has them decoded by then): their H2D copy,
+    # transpose and pyramid build overlap this step's alignment.  Still one H2D of every frame per step, inside the timed
+    # region; the last step has nothing to announce.
+    nxt = lambda k: img_ptrs[k + 1] if k < T else None
     for k in range(1, W + 1):
-        bt.track_raw(ts[k].ctypes.data, dep_ptrs[k], ts[k].ctypes.data, img_ptrs[k], status.ctypes.data, C.addressof(stats))
+        bt.track_raw(ts[k].ctypes.data, dep_ptrs[k], ts[k].ctypes.data, img_ptrs[k], status.ctypes.data, C.addressof(stats), nxt(k))
         gather_poses(bt)
     e2e_switches = 0
     barrier()
     t_start = time.perf_counter()
     for k in range(W + 1, T + 1):
-        bt.track_raw(ts[k].ctypes.data, dep_ptrs[k], ts[k].ctypes.data, img_ptrs[k], status.ctypes.data, C.addressof(stats))
+        bt.track_raw(ts[k].ctypes.data, dep_ptrs[k], ts[k].ctypes.data, img_ptrs[k], status.ctypes.data, C.addressof(stats), nxt(k))
         bt.current_frames()  # device -> host read of the step's result (poses) is part of the call above; this is the accessor
         gather_poses(bt)
         e2e_switches += sum(s.keyframe_changed for s in stats)

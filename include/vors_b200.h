@@ -146,6 +146,14 @@ int vors_batch_create(const vors_config* cfg, uint32_t n, const double* depth_ts
  * failed (see status[i]), negative on error. */
 int vors_batch_track(vors_batch* b, const double* depth_ts, const uint16_t* const* depth,
                      const double* img_ts, const uint8_t* const* img, int* status, vors_track_stats* stats);
+/* Same, and `next_img` (n host pointers, or NULL) announces the frames the NEXT call will be given: their upload and
+ * pyramid build (multires.rs:21-31, run by Tracker::track at inverse_compositional.rs:178) are started on a copy
+ * stream so that they overlap this call's alignment; the next call recognises them by pointer identity and skips its
+ * own upload.  The announced buffers must stay valid and unchanged until that call returns.  An extension: the
+ * reference's track() is strictly sequential. */
+int vors_batch_track_next(vors_batch* b, const double* depth_ts, const uint16_t* const* depth,
+                          const double* img_ts, const uint8_t* const* img, const uint8_t* const* next_img,
+                          int* status, vors_track_stats* stats);
 /* Same with DEVICE-resident inputs in the internal layout (column-major, one image per stream,
  * `img_dev` = n*rows*cols u8 contiguous, `depth_dev` = n*rows*cols u16 contiguous). */
 int vors_batch_track_device(vors_batch* b, const double* depth_ts, const uint16_t* depth_dev,

@@ -512,6 +512,36 @@ def test_large_batch_overlapped_upload_path(vb, oracle):
         _pose_close(poses[i], ot.current_frame()[1].as_array(), oracle)
 
 
+def test_announced_next_frames_give_identical_results(vb):
+    """vors_batch_track_next uploads the announced frames of the next call (and builds their pyramids) on the copy stream
+    while the current frames are aligned.  Poses must be bit-identical to the plain sequential calls, also when an
+    announcement is not honoured (the next call gets other buffers) and across keyframe switches."""
+    n, T = 5, 6
+    seqs = [synth.make_sequence(seed=900 + i, n_frames=T + 1, rows=60, cols=80, step_v=0.02, step_w=0.012) for i in range(n)]
+    cfg = vb.Config(nb_levels=3, **synth.scene_config_kwargs(seqs[0][0]))
+    frames = [np.ascontiguousarray(np.stack([s[1][k][0] for s in seqs])) for k in range(T + 1)]
+    depths = [np.ascontiguousarray(np.stack([s[1][k][1] for s in seqs])) for k in range(T + 1)]
+    decoy = np.ascontiguousarray(frames[3][::-1].copy())  # announced once, never used
+
+    def run(mode):
+        bt = vb.BatchTracker(cfg, np.zeros(n), depths[0], np.zeros(n), frames[0])
+        switches = 0
+        for k in range(1, T + 1):
+            t = np.full(n, float(k))
+            nxt = None
+            if mode == "announce" and k < T:
+                nxt = decoy if k == 2 else frames[k + 1]
+            status, stats = bt.track(t, depths[k], t, frames[k], next_imgs=nxt)
+            assert not status.any()
+            switches += sum(s.keyframe_changed for s in stats)
+        return bt.current_frames()[1], switches
+
+    plain, sw_a = run("plain")
+    ann, sw_b = run("announce")
+    assert sw_a == sw_b and sw_a > 0  # the sequence does switch keyframes
+    assert np.array_equal(plain, ann)
+
+
 # ---- intrinsics variants: skew != 0 (general Jacobian kernel), negative fy (ICL-NUIM), full HD -------------------
 
 def _synth_pair_with_intrinsics(seed, rows, cols, **intr):

@@ -36,17 +36,11 @@ namespace vors {
 
 namespace {
 
-#ifndef VORS_PIPE
-#define VORS_PIPE 0      // 0: back(q) after front(q+1) (longest gather-to-use distance, measured best); 1: between its two halves
+#ifndef VORS_CHUNK_UNROLL
+#define VORS_CHUNK_UNROLL 4
 #endif
 #ifndef VORS_TIMING
 #define VORS_TIMING 0
-#endif
-#ifndef VORS_TOUCH
-#define VORS_TOUCH 0
-#endif
-#ifndef VORS_EXPERIMENT
-#define VORS_EXPERIMENT 0
 #endif
 #ifndef VORS_WARPS
 #define VORS_WARPS 10
@@ -60,6 +54,7 @@ namespace {
 constexpr int kWarps = VORS_WARPS;            // warps per CTA; every warp refills its own TMA ring
 constexpr int kConsumers = kWarps * 32;
 constexpr int kBlock = kConsumers;
+constexpr int kChunkUnroll = VORS_CHUNK_UNROLL;  // chunks of a stage unrolled in the hot loop (instruction-cache footprint)
 constexpr int kSerialWarp = kWarps - 1;       // runs the serial part of every LM round
 constexpr int kMinCtasPerSm = VORS_MIN_CTAS;  // 10 warps x 2 CTAs: register cap 96, 20 warps per SM
 constexpr int kStageChunks = VORS_STAGE_CHUNKS;  // chunk-blocked records per ring stage
@@ -115,9 +110,6 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 // candidates are streamed once per pass: evict-first in L2 so the frame images (re-read by every pass) stay resident
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
     uint64_t pol;
@@ -128,14 +120,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar), "l"(policy)
                  : "memory");
-}
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // non-blocking
-    uint32_t done;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done)
-                 : "r"(bar), "r"(parity)
-                 : "memory");
-    return done != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
@@ -151,7 +135,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // int -> float conversions: I2F on the XU pipe (measured: the ALU pipe is the busier one in this kernel, so the
 // 2-ALU-op magic-number conversion is only used where it fuses with work that is needed anyway).
 __device__ __forceinline__ float u2f(uint32_t v) { return float(v); }
-__device__ __forceinline__ float s16_2f(uint32_t v16) { return float(int(short(v16))); }
 // 1/x: MUFU.RCP seed + one Newton step (2 FMAs) = correctly rounded to within 1 ulp without the slow-path range
 // checks of an IEEE division; x = 0 / inf / NaN give inf / NaN, which the inside test rejects like the reference.
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -404,7 +387,6 @@ __device__ __noinline__ void deferred_pass(int warp, int lane, int first_stage, 
 struct PassConst {
     float cx, cy, su, sv, lim_lo, magic_u, magic_v, zero_u, zero_v;
     uint32_t rows;
-    uint32_t touch;
     const uint8_t* img_biased;
 };
 
@@ -476,7 +458,7 @@ __device__ __forceinline__ FrontA front_a(uint32_t pk, float rho, uint32_t gr, c
 // `word` is the bitmap word of this call's 32 slots.
 // `old_words`: lane j holds the far-bitmap word of the stage's word j from the previous pass of the level; bit j of
 // `old_nz` says whether it is non-zero.  `j` = this call's word within the stage.
-template <bool kSkew, bool kTouch>
+template <bool kSkew>
 __device__ __forceinline__ void front_b(const FrontA& x, int word, int j, unsigned old_words, unsigned old_nz, const PassConst& lc,
                                         const Intrinsics& k, Defer& df, float* hs, int lane, Front& f) {
     uint32_t pk = x.pk;
@@ -528,15 +510,6 @@ __device__ __forceinline__ void front_b(const FrontA& x, int word, int j, unsign
     f.t10 = __ldg(p + 1);
     f.t01 = __ldg(p + lc.rows);
     f.t11 = __ldg(p + lc.rows + 1);
-#if VORS_TOUCH
-    // pull the image lines of this warp's next stage into L1 now (dense candidates in scan order: one team-stride of
-    // stages later = that many bytes further in the column-major image; harmless for sparse candidates)
-    if (kTouch) {
-        uint32_t d0, d1;
-        asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(d0) : "l"(p + lc.touch));
-        asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(d1) : "l"(p + lc.touch + lc.rows));
-    }
-#endif
     f.pk = pk;
     f.gr = x.gr;
     f.a = x.a;
@@ -782,7 +755,6 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                     lc.cx = s_lc.cx; lc.cy = s_lc.cy; lc.su = s_lc.su; lc.sv = s_lc.sv; lc.lim_lo = s_lc.lim_lo;
                     lc.magic_u = s_lc.magic_u; lc.magic_v = s_lc.magic_v; lc.rows = s_lc.rows; lc.img_biased = s_lc.img_biased;
                     lc.zero_u = s_lc.zero_u; lc.zero_v = s_lc.zero_v;
-                    lc.touch = uint32_t(TW * kStageCand);
                     const Intrinsics k = s_lc.k;
                     Acc acc;
                     acc.e = 0.0f;
@@ -839,24 +811,14 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                         if (lane < kStageWordsBm && !df.first_pass && c + TW < n_stages) old_next = __ldcg(df.far + kStageWordsBm * (c + TW) + lane);
                         const float* sp = &S.ring[warp][ring_slot * kStageWords] + lane;
                         // word j of the stage = 32 consecutive candidates (chunk j / 2, half j % 2), one per lane
-#if VORS_PIPE == 1
 #define VORS_STEP(CH, HALF, FNEW, FOLD)                                                               \
     {                                                                                                 \
         const float* q = sp + (CH) * 3 * kChunk + (HALF) * 32;                                        \
         const FrontA xa = front_a(__float_as_uint(q[0]), q[kChunk], __float_as_uint(q[2 * kChunk]), M, lc); \
-        back<kSkew>(FOLD, k, acc);                                                                    \
-        front_b<kSkew, false>(xa, kStageWordsBm * c + 2 * (CH) + (HALF), 2 * (CH) + (HALF), old_words, old_nz, lc, k, df, hs, lane, FNEW); \
-    }
-#else
-#define VORS_STEP(CH, HALF, FNEW, FOLD)                                                               \
-    {                                                                                                 \
-        const float* q = sp + (CH) * 3 * kChunk + (HALF) * 32;                                        \
-        const FrontA xa = front_a(__float_as_uint(q[0]), q[kChunk], __float_as_uint(q[2 * kChunk]), M, lc); \
-        front_b<kSkew, false>(xa, kStageWordsBm * c + 2 * (CH) + (HALF), 2 * (CH) + (HALF), old_words, old_nz, lc, k, df, hs, lane, FNEW); \
+        front_b<kSkew>(xa, kStageWordsBm * c + 2 * (CH) + (HALF), 2 * (CH) + (HALF), old_words, old_nz, lc, k, df, hs, lane, FNEW); \
         back<kSkew>(FOLD, k, acc);                                                                    \
     }
-#endif
-#pragma unroll
+#pragma unroll(kChunkUnroll)
                         for (int ch = 0; ch < kStageChunks; ++ch) {
                             VORS_STEP(ch, 0, fa, fb)
                             VORS_STEP(ch, 1, fb, fa)

@@ -103,8 +103,16 @@ class Engine {
     bool tracing = false;
 
     // device slabs ([n] x per-stream extent)
-    uint8_t* d_pyr = nullptr;        // frame pyramid, pix_total per stream
-    uint8_t* d_stage8 = nullptr;     // row-major staging, rows*cols per stream
+    uint8_t* d_pyr = nullptr;        // frame pyramid of the frame being tracked, pix_stride per stream
+    uint8_t* d_stage8 = nullptr;     // its row-major staging, rows*cols per stream
+    // second set: the frames announced for the NEXT track call are uploaded (and their pyramids built) here on the copy
+    // stream while the current frames are being aligned; the sets swap when that call arrives
+    uint8_t* d_pyr_alt = nullptr;
+    uint8_t* d_stage8_alt = nullptr;
+    AlignJob* d_jobs_alt = nullptr;  // job descriptors pointing into d_pyr_alt
+    bool pending = false;            // d_pyr_alt holds prefetched frames
+    std::vector<const uint8_t*> pending_ptrs;
+    cudaEvent_t ev_pref{};
     uint16_t* d_stage16 = nullptr;   // row-major depth staging (launch order)
     uint16_t* d_depth = nullptr;     // column-major depth, rows*cols per stream
     uint32_t* d_grad = nullptr;      // gradient pairs of all levels
@@ -146,7 +154,7 @@ class Engine {
     void destroy() {
         DeviceScope scope(device);
         if (L.stream) cudaStreamSynchronize(L.stream);
-        void* dev_ptrs[] = {d_pyr, d_stage8, d_stage16, d_depth, d_grad, d_g2, d_mask, d_idepth, d_weight, d_pts, d_defer,
+        void* dev_ptrs[] = {d_pyr, d_stage8, d_pyr_alt, d_stage8_alt, d_jobs_alt, d_stage16, d_depth, d_grad, d_g2, d_mask, d_idepth, d_weight, d_pts, d_defer,
                             d_blk_count, d_n_points, d_h_total, d_items, d_jobs, d_init, d_results, d_scratch, d_trace, d_tmp, d_gradmag, d_dso_ws};
         for (void* p : dev_ptrs)
             if (p) cudaFree(p);
@@ -155,6 +163,8 @@ class Engine {
             if (p) cudaFreeHost(p);
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
+        if (ev_pref) cudaEventDestroy(ev_pref);
+        ev_pref = nullptr;
         for (auto& e : ev_up)
             if (e) cudaEventDestroy(e);
         if (LC.stream) cudaStreamDestroy(LC.stream);
@@ -221,6 +231,7 @@ class Engine {
         CU_TRY(cudaStreamCreateWithFlags(&LC.stream, cudaStreamNonBlocking));
         for (auto& e : ev) CU_TRY(cudaEventCreate(&e));
         for (auto& e : ev_up) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&ev_pref, cudaEventDisableTiming));
         CU_TRY(align_query(&info));
         if (info.max_resident_ctas < 1) return fail(VORS_E_CUDA, "align kernel cannot be resident on this device");
 
@@ -229,6 +240,10 @@ class Engine {
         CU_TRY(cudaMalloc(&d_pyr, N * P + (size_t(1) << 20)));
         CU_TRY(cudaMemsetAsync(d_pyr, 0, N * P + (size_t(1) << 20), L.stream));  // the zero page of every slab stays zero: no kernel writes it
         CU_TRY(cudaMalloc(&d_stage8, N * I));
+        CU_TRY(cudaMalloc(&d_pyr_alt, N * P + (size_t(1) << 20)));
+        CU_TRY(cudaMemsetAsync(d_pyr_alt, 0, N * P + (size_t(1) << 20), L.stream));
+        CU_TRY(cudaMalloc(&d_stage8_alt, N * I));
+        CU_TRY(cudaMalloc(&d_jobs_alt, N * sizeof(AlignJob)));
         CU_TRY(cudaMalloc(&d_stage16, N * I * 2));
         CU_TRY(cudaMalloc(&d_depth, N * I * 2));
         CU_TRY(cudaMalloc(&d_grad, N * P * 4));
@@ -267,6 +282,11 @@ class Engine {
         st.assign(N, StreamState{});
 
         // static part of the job descriptors: full alignment of stream i against its keyframe
+        std::swap(d_pyr, d_pyr_alt);
+        for (int i = 0; i < n; ++i) fill_job(h_jobs[i], i, levels - 1, 0, levels - 1, 0);
+        CU_TRY(cudaMemcpyAsync(d_jobs_alt, h_jobs, N * sizeof(AlignJob), cudaMemcpyHostToDevice, L.stream));
+        CU_TRY(cudaStreamSynchronize(L.stream));
+        std::swap(d_pyr, d_pyr_alt);
         for (int i = 0; i < n; ++i) fill_job(h_jobs[i], i, levels - 1, 0, levels - 1, 0);
         CU_TRY(cudaMemcpyAsync(d_jobs, h_jobs, N * sizeof(AlignJob), cudaMemcpyHostToDevice, L.stream));
         CU_TRY(cudaStreamSynchronize(L.stream));
@@ -300,11 +320,12 @@ class Engine {
 
     // ---- uploads ------------------------------------------------------------------------------
     // Frames of streams [start, start + m) into level 0 of their frame pyramids (column-major), on launcher X's stream.
-    int upload_images_host_range(const uint8_t* const* img, int start, int m, Launcher& X) {
+    int upload_images_host_range(const uint8_t* const* img, int start, int m, Launcher& X, uint8_t* pyr_slab = nullptr,
+                                 uint8_t* stage_slab = nullptr) {
         const size_t I = size_t(rows) * cols;
         bool contiguous = true;
         for (int i = 1; i < m && contiguous; ++i) contiguous = (img[start + i] == img[start] + size_t(i) * I);
-        uint8_t* pyr0 = d_pyr + size_t(start) * g.pix_stride;
+        uint8_t* pyr0 = (pyr_slab ? pyr_slab : d_pyr) + size_t(start) * g.pix_stride;
         if (layout == VORS_COL_MAJOR) {
             if (contiguous) {
                 CU_TRY(cudaMemcpy2DAsync(pyr0, size_t(g.pix_stride), img[start], I, I, size_t(m), cudaMemcpyHostToDevice, X.stream));
@@ -313,7 +334,7 @@ class Engine {
                     CU_TRY(cudaMemcpyAsync(pyr0 + size_t(i) * g.pix_stride, img[start + i], I, cudaMemcpyHostToDevice, X.stream));
             }
         } else {
-            uint8_t* stage = d_stage8 + size_t(start) * I;
+            uint8_t* stage = (stage_slab ? stage_slab : d_stage8) + size_t(start) * I;
             if (contiguous) {
                 CU_TRY(cudaMemcpyAsync(stage, img[start], I * size_t(m), cudaMemcpyHostToDevice, X.stream));
             } else {
@@ -466,8 +487,11 @@ class Engine {
     }
 
     // n x Tracker::track (inverse_compositional.rs:170-240)
+    // `next_img` (optional, host frames): the frames the NEXT call will be given; their upload and pyramid build then
+    // overlap this call's alignment.
     int track(const double* depth_ts, const uint16_t* const* depth, const uint16_t* depth_dev, const double* img_ts,
-              const uint8_t* const* img, const uint8_t* img_dev, int* status, vors_track_stats* stats) {
+              const uint8_t* const* img, const uint8_t* img_dev, int* status, vors_track_stats* stats,
+              const uint8_t* const* next_img = nullptr) {
         DEVICE_SCOPE(device);
         const unsigned long long launches0 = L.launches + LC.launches;
         int rc;
@@ -480,8 +504,19 @@ class Engine {
         // Host frames of a large batch are processed as two half batches: the H2D copy (+ transpose) of the second half
         // runs on the copy stream while the first half is being aligned (each half still fills the device: the align
         // kernel spreads every alignment over cap / (n/2) CTAs).  SURVEY §8f rank 2.
-        const int n_chunks = (!img_dev && n >= 64 && cfg.team_size == 0) ? 2 : 1;
-        if (img_dev) {
+        // were these frames announced by the previous call?  Then they (and their pyramids) are already on the device.
+        bool prefetched = pending && !img_dev && img;
+        for (int i = 0; prefetched && i < n; ++i) prefetched = (img[i] == pending_ptrs[size_t(i)]);
+        pending = false;
+        if (prefetched) {
+            std::swap(d_pyr, d_pyr_alt);
+            std::swap(d_stage8, d_stage8_alt);
+            std::swap(d_jobs, d_jobs_alt);
+            CU_TRY(cudaStreamWaitEvent(L.stream, ev_pref, 0));
+        }
+        const int n_chunks = (!prefetched && !img_dev && n >= 64 && cfg.team_size == 0) ? 2 : 1;
+        if (prefetched) {
+        } else if (img_dev) {
             if ((rc = upload_images_device(img_dev)) != VORS_OK) return rc;
         } else {
             if (!img) return fail(VORS_E_INVALID, "null image pointer array");
@@ -501,7 +536,7 @@ class Engine {
         }
         CU_TRY(cudaEventRecord(ev[1], L.stream));
         if (n_chunks == 1) {
-            launch_pyramid(L, g, d_pyr, nullptr, n);  // :178
+            if (!prefetched) launch_pyramid(L, g, d_pyr, nullptr, n);  // :178
             CU_TRY(cudaEventRecord(ev[2], L.stream));
             if ((rc = run_align(n, max_points)) != VORS_OK) return rc;  // :181-201
         } else {
@@ -515,6 +550,17 @@ class Engine {
         }
         CU_TRY(cudaEventRecord(ev[3], L.stream));
         CU_TRY(cudaMemcpyAsync(h_results, d_results, size_t(n) * sizeof(AlignResult), cudaMemcpyDeviceToHost, L.stream));
+        if (next_img) {
+            // the other set is idle (everything earlier calls did with it has completed): stage the next frames there on the
+            // copy stream while the align kernel runs
+            for (int i = 0; i < n; ++i)
+                if (!next_img[i]) return fail(VORS_E_INVALID, "null next-image pointer");
+            if ((rc = upload_images_host_range(next_img, 0, n, LC, d_pyr_alt, d_stage8_alt)) != VORS_OK) return rc;
+            launch_pyramid(LC, g, d_pyr_alt, nullptr, n);
+            CU_TRY(cudaEventRecord(ev_pref, LC.stream));
+            pending_ptrs.assign(next_img, next_img + n);
+            pending = true;
+        }
         CU_TRY(cudaStreamSynchronize(L.stream));
 
         int m = 0;
@@ -746,6 +792,12 @@ int vors_batch_track(vors_batch* b, const double* depth_ts, const uint16_t* cons
                      const uint8_t* const* img, int* status, vors_track_stats* stats) {
     if (!b) return fail(VORS_E_INVALID, "null batch");
     return b->e->track(depth_ts, depth, nullptr, img_ts, img, nullptr, status, stats);
+}
+
+int vors_batch_track_next(vors_batch* b, const double* depth_ts, const uint16_t* const* depth, const double* img_ts,
+                          const uint8_t* const* img, const uint8_t* const* next_img, int* status, vors_track_stats* stats) {
+    if (!b) return fail(VORS_E_INVALID, "null batch");
+    return b->e->track(depth_ts, depth, nullptr, img_ts, img, nullptr, status, stats, next_img);
 }
 
 int vors_batch_track_device(vors_batch* b, const double* depth_ts, const uint16_t* depth_dev, const double* img_ts,

@@ -99,6 +99,7 @@ SIGNATURES = {
     "vors_tracker_destroy": (None, [_vp]),
     "vors_batch_create": (C.c_int, [_P(ConfigStruct), C.c_uint32, _vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_int, _P(_vp)]),
     "vors_batch_track": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vors_batch_track_next": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vors_batch_track_device": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vors_batch_current_frames": (C.c_int, [_vp, _vp, _vp]),
     "vors_batch_size": (C.c_int, [_vp]),
@@ -285,8 +286,9 @@ class BatchTracker:
     def set_tracing(self, enabled=True):
         _check(self._lib.vors_batch_set_tracing(self._h, int(enabled)))
 
-    def track(self, depth_ts, depths, img_ts, imgs):
-        """Host buffers [n, rows, cols]; returns (status[n], stats list)."""
+    def track(self, depth_ts, depths, img_ts, imgs, next_imgs=None):
+        """Host buffers [n, rows, cols]; returns (status[n], stats list).  `next_imgs`: the C-contiguous uint8 array the NEXT
+        call will be given as `imgs` (same object): its upload then overlaps this call's alignment."""
         imgs = np.ascontiguousarray(imgs, np.uint8)
         depths = np.ascontiguousarray(depths, np.uint16)
         dts = np.ascontiguousarray(depth_ts, np.float64)
@@ -294,11 +296,22 @@ class BatchTracker:
         ip, dp = self._ptr_arrays(imgs, depths)
         status = np.zeros(self.n, np.int32)
         stats = (TrackStats * self.n)()
-        _check(self._lib.vors_batch_track(self._h, _ptr(dts), dp, _ptr(its), ip, _ptr(status), stats), True)
+        if next_imgs is not None:
+            if not (isinstance(next_imgs, np.ndarray) and next_imgs.dtype == np.uint8 and next_imgs.flags.c_contiguous):
+                raise ValueError("next_imgs must be a C-contiguous uint8 array (it is recognised by address in the next call)")
+            self._announced = next_imgs  # keep the announced buffer alive until the next call
+            nip, _ = self._ptr_arrays(next_imgs, depths)
+            _check(self._lib.vors_batch_track_next(self._h, _ptr(dts), dp, _ptr(its), ip, nip, _ptr(status), stats), True)
+        else:
+            _check(self._lib.vors_batch_track(self._h, _ptr(dts), dp, _ptr(its), ip, _ptr(status), stats), True)
         return status, list(stats)
 
-    def track_raw(self, dts_ptr, depth_ptrs, its_ptr, img_ptrs, status_ptr=None, stats_ptr=None):
-        """Pre-marshalled pointers (bench hot loop): no numpy work inside the timed region."""
+    def track_raw(self, dts_ptr, depth_ptrs, its_ptr, img_ptrs, status_ptr=None, stats_ptr=None, next_img_ptrs=None):
+        """Pre-marshalled pointers (bench hot loop): no numpy work inside the timed region.  `next_img_ptrs` announces the
+        frames of the next call (their upload then overlaps this call's alignment)."""
+        if next_img_ptrs is not None:
+            return _check(self._lib.vors_batch_track_next(self._h, dts_ptr, depth_ptrs, its_ptr, img_ptrs, next_img_ptrs, status_ptr,
+                                                          stats_ptr), True)
         return _check(self._lib.vors_batch_track(self._h, dts_ptr, depth_ptrs, its_ptr, img_ptrs, status_ptr, stats_ptr), True)
 
     def track_device(self, dts_ptr, depth_dev_ptr, its_ptr, img_dev_ptr, status_ptr=None, stats_ptr=None):
