@@ -55,6 +55,7 @@ constexpr int kWarps = VORS_WARPS;            // warps per CTA; every warp refil
 constexpr int kConsumers = kWarps * 32;
 constexpr int kBlock = kConsumers;
 constexpr int kChunkUnroll = VORS_CHUNK_UNROLL;  // chunks of a stage unrolled in the hot loop (instruction-cache footprint)
+constexpr int kSmallWordsPerWarp = 4;           // levels of at most this many 32-candidate words per warp skip the TMA ring
 constexpr int kSerialWarp = kWarps - 1;       // runs the serial part of every LM round
 constexpr int kMinCtasPerSm = VORS_MIN_CTAS;  // 10 warps x 2 CTAs: register cap 96, 20 warps per SM
 constexpr int kStageChunks = VORS_STAGE_CHUNKS;  // chunk-blocked records per ring stage
@@ -777,57 +778,80 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                     Front fa, fb;
                     fb.pk = 0u; fb.gr = 0u; fb.a = 0.0f; fb.b = 0.0f; fb.rho = 0.0f; fb.fa = 0.0f; fb.fb = 0.0f;
                     fb.t00 = fb.t10 = fb.t01 = fb.t11 = 0u;
-                    // every warp streams its own stages (gw, gw + TW, ...) through its ring: lane 0 issues one bulk copy
-                    // per stage, kStages - 1 stages ahead of the one being consumed (SASS UBLKCP + SYNCS)
-                    if (lane == 0) {
-                        uint32_t slot = ring_slot;
-                        for (int j = 0, c = gw; j < kStages - 1 && c < n_stages; ++j, c += TW) {
-                            const uint32_t bar = bar_base + slot * 8u;
-                            mbar_expect_tx(bar, kStageBytes);
-                            bulk_g2s(ring_base + slot * kStageBytes, pts + size_t(c) * kStageWords, kStageBytes, bar, l2_policy);
-                            slot = (slot + 1 == kStages) ? 0u : slot + 1;
+                    const int n_words = n_stages * kStageWordsBm;  // 32-slot words of the level (padding included)
+                    if (n_words <= kSmallWordsPerWarp * TW) {
+                        // ---- small level: a 256-candidate stage per warp would leave most warps idle and the rest with
+                        // eight dependent word-steps, so the words are dealt round-robin to all warps and read straight from
+                        // global memory (three coalesced loads per word); same front / back arithmetic, no pipelining.
+                        for (int wi = gw; wi < n_words; wi += TW) {
+                            const uint32_t* rec = pts + size_t(wi >> 1) * (3 * kChunk) + 32 * (wi & 1) + lane;
+                            const uint32_t pk = __ldg(rec), gr = __ldg(rec + 2 * kChunk);
+                            const float rho = __uint_as_float(__ldg(rec + kChunk));
+                            unsigned old = 0u;
+                            if (df.first_pass) {
+                                if (lane == 0) df.far[wi] = 0u;
+                                __syncwarp();
+                            } else {
+                                old = __ldcg(df.far + wi);
+                            }
+                            const FrontA xa = front_a(pk, rho, gr, M, lc);
+                            front_b<kSkew>(xa, wi, 0, old, old != 0u ? 1u : 0u, lc, k, df, hs, lane, fa);
+                            back<kSkew>(fa, k, acc);
+                            n_slots += 32;
                         }
-                    }
-                    if (df.first_pass) {  // the level's far bitmap starts empty: clear the words of this warp's stages
-                        for (int c = gw; c < n_stages; c += TW)
-                            if (lane < kStageWordsBm) df.far[kStageWordsBm * c + lane] = 0u;
-                        __syncwarp();  // orders these stores before lane 0's later stores to the same words
-                    }
-                    // the stage's far-bitmap words of the previous pass (one per lane 0..kStageWordsBm-1), fetched one iteration ahead
-                    unsigned old_next = (lane < kStageWordsBm && !df.first_pass && gw < n_stages) ? __ldcg(df.far + kStageWordsBm * gw + lane) : 0u;
-                    for (int c = gw; c < n_stages; c += TW) {
-                        // refill the slot freed by the previous iteration (every lane consumed its loads before that
-                        // iteration's trailing __syncwarp) with the stage kStages - 1 ahead
-                        const int c_ahead = c + (kStages - 1) * TW;
-                        if (lane == 0 && c_ahead < n_stages) {
-                            const uint32_t slot = (ring_slot + kStages - 1 >= kStages) ? ring_slot - 1 : ring_slot + kStages - 1;
-                            const uint32_t bar = bar_base + slot * 8u;
-                            mbar_expect_tx(bar, kStageBytes);
-                            bulk_g2s(ring_base + slot * kStageBytes, pts + size_t(c_ahead) * kStageWords, kStageBytes, bar, l2_policy);
+                    } else {
+                        // every warp streams its own stages (gw, gw + TW, ...) through its ring: lane 0 issues one bulk copy
+                        // per stage, kStages - 1 stages ahead of the one being consumed (SASS UBLKCP + SYNCS)
+                        if (lane == 0) {
+                            uint32_t slot = ring_slot;
+                            for (int j = 0, c = gw; j < kStages - 1 && c < n_stages; ++j, c += TW) {
+                                const uint32_t bar = bar_base + slot * 8u;
+                                mbar_expect_tx(bar, kStageBytes);
+                                bulk_g2s(ring_base + slot * kStageBytes, pts + size_t(c) * kStageWords, kStageBytes, bar, l2_policy);
+                                slot = (slot + 1 == kStages) ? 0u : slot + 1;
+                            }
                         }
-                        mbar_wait(bar_base + ring_slot * 8u, ring_parity);  // TMA bytes have landed
-                        const unsigned old_words = old_next;
-                        const unsigned old_nz = __ballot_sync(0xffffffffu, old_words != 0u);
-                        if (lane < kStageWordsBm && !df.first_pass && c + TW < n_stages) old_next = __ldcg(df.far + kStageWordsBm * (c + TW) + lane);
-                        const float* sp = &S.ring[warp][ring_slot * kStageWords] + lane;
-                        // word j of the stage = 32 consecutive candidates (chunk j / 2, half j % 2), one per lane
-#define VORS_STEP(CH, HALF, FNEW, FOLD)                                                               \
-    {                                                                                                 \
-        const float* q = sp + (CH) * 3 * kChunk + (HALF) * 32;                                        \
-        const FrontA xa = front_a(__float_as_uint(q[0]), q[kChunk], __float_as_uint(q[2 * kChunk]), M, lc); \
-        front_b<kSkew>(xa, kStageWordsBm * c + 2 * (CH) + (HALF), 2 * (CH) + (HALF), old_words, old_nz, lc, k, df, hs, lane, FNEW); \
-        back<kSkew>(FOLD, k, acc);                                                                    \
-    }
-#pragma unroll(kChunkUnroll)
-                        for (int ch = 0; ch < kStageChunks; ++ch) {
-                            VORS_STEP(ch, 0, fa, fb)
-                            VORS_STEP(ch, 1, fb, fa)
+                        if (df.first_pass) {  // the level's far bitmap starts empty: clear the words of this warp's stages
+                            for (int c = gw; c < n_stages; c += TW)
+                                if (lane < kStageWordsBm) df.far[kStageWordsBm * c + lane] = 0u;
+                            __syncwarp();  // orders these stores before lane 0's later stores to the same words
                         }
-#undef VORS_STEP
-                        __syncwarp();  // all lanes are done with this slot: the next iteration may refill it
-                        ring_slot = (ring_slot + 1 == kStages) ? 0u : ring_slot + 1;
-                        ring_parity ^= (ring_slot == 0) ? 1u : 0u;
-                        n_slots += kStageCand;
+                        // the stage's far-bitmap words of the previous pass (one per lane 0..kStageWordsBm-1), fetched one iteration ahead
+                        unsigned old_next = (lane < kStageWordsBm && !df.first_pass && gw < n_stages) ? __ldcg(df.far + kStageWordsBm * gw + lane) : 0u;
+                        for (int c = gw; c < n_stages; c += TW) {
+                            // refill the slot freed by the previous iteration (every lane consumed its loads before that
+                            // iteration's trailing __syncwarp) with the stage kStages - 1 ahead
+                            const int c_ahead = c + (kStages - 1) * TW;
+                            if (lane == 0 && c_ahead < n_stages) {
+                                const uint32_t slot = (ring_slot + kStages - 1 >= kStages) ? ring_slot - 1 : ring_slot + kStages - 1;
+                                const uint32_t bar = bar_base + slot * 8u;
+                                mbar_expect_tx(bar, kStageBytes);
+                                bulk_g2s(ring_base + slot * kStageBytes, pts + size_t(c_ahead) * kStageWords, kStageBytes, bar, l2_policy);
+                            }
+                            mbar_wait(bar_base + ring_slot * 8u, ring_parity);  // TMA bytes have landed
+                            const unsigned old_words = old_next;
+                            const unsigned old_nz = __ballot_sync(0xffffffffu, old_words != 0u);
+                            if (lane < kStageWordsBm && !df.first_pass && c + TW < n_stages) old_next = __ldcg(df.far + kStageWordsBm * (c + TW) + lane);
+                            const float* sp = &S.ring[warp][ring_slot * kStageWords] + lane;
+                            // word j of the stage = 32 consecutive candidates (chunk j / 2, half j % 2), one per lane
+    #define VORS_STEP(CH, HALF, FNEW, FOLD)                                                               \
+        {                                                                                                 \
+            const float* q = sp + (CH) * 3 * kChunk + (HALF) * 32;                                        \
+            const FrontA xa = front_a(__float_as_uint(q[0]), q[kChunk], __float_as_uint(q[2 * kChunk]), M, lc); \
+            front_b<kSkew>(xa, kStageWordsBm * c + 2 * (CH) + (HALF), 2 * (CH) + (HALF), old_words, old_nz, lc, k, df, hs, lane, FNEW); \
+            back<kSkew>(FOLD, k, acc);                                                                    \
+        }
+    #pragma unroll(kChunkUnroll)
+                            for (int ch = 0; ch < kStageChunks; ++ch) {
+                                VORS_STEP(ch, 0, fa, fb)
+                                VORS_STEP(ch, 1, fb, fa)
+                            }
+    #undef VORS_STEP
+                            __syncwarp();  // all lanes are done with this slot: the next iteration may refill it
+                            ring_slot = (ring_slot + 1 == kStages) ? 0u : ring_slot + 1;
+                            ring_parity ^= (ring_slot == 0) ? 1u : 0u;
+                            n_slots += kStageCand;
+                        }
                     }
                     back<kSkew>(fb, k, acc);
 #if VORS_TIMING

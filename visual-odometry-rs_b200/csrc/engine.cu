@@ -459,15 +459,16 @@ class Engine {
     }
 
     // CTAs per alignment: 1 when the batch alone fills the device, otherwise spread each alignment over enough CTAs for
-    // ~16 level-0 candidates per thread (measured: per-pass barrier + partial-sum cost grows with the team, so sparse
-    // coarse-to-fine keyframes want 1-5 CTAs and a dense 640x480 keyframe ~64), bounded by what can be co-resident.
+    // ~8 level-0 candidates per thread, and keep small keyframes (< 10 k candidates) on one CTA (measured,
+    // scripts/latency_breakdown.py: the per-pass team barrier costs more than such a keyframe's whole hot loop; a 1080p
+    // coarse-to-fine keyframe wants ~8 CTAs, a dense 640x480 one 64+), bounded by what can be co-resident.
     void choose_team(int n_jobs, int max_points, int* team, int* n_teams) const {
         const int cap = info.max_resident_ctas;
         int t = 1;
         if (cfg.team_size) {
             t = int(cfg.team_size);
         } else if (n_jobs < cap) {
-            const int by_points = (max_points + info.block * 16 - 1) / (info.block * 16);
+            const int by_points = max_points < 10000 ? 1 : (max_points + info.block * 8 - 1) / (info.block * 8);
             t = std::max(1, std::min(std::min(cap / n_jobs, by_points), 64));
         }
         t = std::max(1, std::min(t, std::min(kMaxTeam, cap)));
