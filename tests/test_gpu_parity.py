@@ -512,6 +512,22 @@ def test_large_batch_overlapped_upload_path(vb, oracle):
         _pose_close(poses[i], ot.current_frame()[1].as_array(), oracle)
 
 
+@pytest.mark.parametrize("shape", [(64, 96), (128, 80), (144, 176)])
+def test_tracker_levels_with_power_of_two_and_odd_row_counts(vb, oracle, shape):
+    """The align kernel folds the bit pattern of its floor constants into the image base pointer (mod 2^32); the constant
+    depends on the level's row count.  16-, 32- and 64-row levels (and 18 / 36 / 72) exercise its extremes."""
+    rows, cols = shape
+    scene, frames, _ = synth.make_sequence(seed=321, n_frames=4, rows=rows, cols=cols, step_v=0.01, step_w=0.006)
+    cfg, ocfg = _cfgs(vb, oracle, scene, nb_levels=3)
+    t = cfg.init(0.0, frames[0][1], 0.0, frames[0][0])
+    ot = oracle.Tracker(ocfg, 0.0, frames[0][1], 0.0, frames[0][0])
+    for k in range(1, 4):
+        st = t.track(float(k), frames[k][1], float(k), frames[k][0])
+        ost = ot.track(float(k), frames[k][1], float(k), frames[k][0])
+        assert st.status == ost[1].status == 0
+        _pose_close(t.current_frame()[1].as_array(), ot.current_frame()[1].as_array(), oracle)
+
+
 def test_announced_next_frames_give_identical_results(vb):
     """vors_batch_track_next uploads the announced frames of the next call (and builds their pyramids) on the copy stream
     while the current frames are aligned.  Poses must be bit-identical to the plain sequential calls, also when an

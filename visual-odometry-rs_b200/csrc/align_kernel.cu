@@ -230,13 +230,16 @@ struct LevelConst {
     double inv_fx, inv_fy, k01;  // 1/fx, 1/fy, -s/(fx fy): the f64 divisions of the per-pass serial part, done once per level
 };
 
-// Chooses Cu so that (bits(Cu) * rows + bits(Cv)) mod 2^32 plus any texel offset of the slab (< 2^27) cannot wrap.
+// Chooses Cu so that (bits(Cu) * rows + bits(Cv)) mod 2^32 plus any texel offset the level can produce (its image and the
+// slab's zero page: at most zero_u * rows + zero_v + rows + 1) cannot wrap.  The shift Cu - 2^23 stays far below 2^22
+// (it is about the slab extent divided by the level's rows), so u + Cu stays inside [2^23, 2^24) where floats are integers.
 __device__ __forceinline__ void choose_floor_magic(LevelConst& c, const uint8_t* img) {
+    const uint32_t max_off = uint32_t(c.zero_u) * c.rows + uint32_t(c.zero_v) + c.rows + 2u;
     uint32_t du = 0u;
     const uint32_t bv = kMagicBits;
-    uint32_t c32 = (kMagicBits + du) * c.rows + bv;
-    if (c32 >= 0xF8000000u) {  // shift the constant past the wrap-around: adds du * rows >= 2^27
-        du = (0x08000000u + c.rows - 1u) / c.rows;
+    uint32_t c32 = kMagicBits * c.rows + bv;
+    if (c32 > 0xFFFFFFFFu - max_off) {  // shift the constant past the wrap-around
+        du = (max_off + c.rows - 1u) / c.rows + 1u;
         c32 = (kMagicBits + du) * c.rows + bv;
     }
     c.magic_u = __uint_as_float(kMagicBits + du);
