@@ -837,19 +837,19 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                             if (lane < kStageWordsBm && !df.first_pass && c + TW < n_stages) old_next = __ldcg(df.far + kStageWordsBm * (c + TW) + lane);
                             const float* sp = &S.ring[warp][ring_slot * kStageWords] + lane;
                             // word j of the stage = 32 consecutive candidates (chunk j / 2, half j % 2), one per lane
-    #define VORS_STEP(CH, HALF, FNEW, FOLD)                                                               \
-        {                                                                                                 \
-            const float* q = sp + (CH) * 3 * kChunk + (HALF) * 32;                                        \
-            const FrontA xa = front_a(__float_as_uint(q[0]), q[kChunk], __float_as_uint(q[2 * kChunk]), M, lc); \
-            front_b<kSkew>(xa, kStageWordsBm * c + 2 * (CH) + (HALF), 2 * (CH) + (HALF), old_words, old_nz, lc, k, df, hs, lane, FNEW); \
-            back<kSkew>(FOLD, k, acc);                                                                    \
-        }
-    #pragma unroll(kChunkUnroll)
+#define VORS_STEP(CH, HALF, FNEW, FOLD)                                                               \
+    {                                                                                                 \
+        const float* q = sp + (CH) * 3 * kChunk + (HALF) * 32;                                        \
+        const FrontA xa = front_a(__float_as_uint(q[0]), q[kChunk], __float_as_uint(q[2 * kChunk]), M, lc); \
+        front_b<kSkew>(xa, kStageWordsBm * c + 2 * (CH) + (HALF), 2 * (CH) + (HALF), old_words, old_nz, lc, k, df, hs, lane, FNEW); \
+        back<kSkew>(FOLD, k, acc);                                                                    \
+    }
+#pragma unroll(kChunkUnroll)
                             for (int ch = 0; ch < kStageChunks; ++ch) {
                                 VORS_STEP(ch, 0, fa, fb)
                                 VORS_STEP(ch, 1, fb, fa)
                             }
-    #undef VORS_STEP
+#undef VORS_STEP
                             __syncwarp();  // all lanes are done with this slot: the next iteration may refill it
                             ring_slot = (ring_slot + 1 == kStages) ? 0u : ring_slot + 1;
                             ring_parity ^= (ring_slot == 0) ? 1u : 0u;
