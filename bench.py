@@ -7,7 +7,8 @@ RGB-D streams, dense candidates (every pixel with depth != 0), 5 levels, 10 fixe
 One step = every stream tracks its next frame = B alignments in ONE persistent kernel launch.
 
   value   frames/s with the step's inputs already resident in HBM (vors_batch_track_device)
-  e2e     frames/s through the C ABI with HOST buffers (vors_batch_track): pinned row-major frames in,
+  e2e     frames/s through the C ABI with HOST buffers (vors_batch_track_next: every call announces the next step's frames
+          so that their upload overlaps the alignment): pinned row-major frames in,
           poses out, H2D/D2H copies inside the timed region
   roofline   align kernel: algorithmic bytes (10 B per candidate-pass) / its device time
   cpu_baseline  the C++ oracle (a restatement of the reference's algorithm, not rustc output), 1 core,
