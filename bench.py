@@ -211,8 +211,9 @@ def run_ours(args):
     # ---- arm 1: inputs resident in HBM ------------------------------------------------------------------
     bt = new_tracker()
     def step_device(k):
+        # the next step's device buffer is announced: its copy into the frame pyramids and the pyramid build overlap this alignment
         return bt.track_device(ts[k].ctypes.data, depth_cm[k].data_ptr(), ts[k].ctypes.data, gray_cm[k].data_ptr(),
-                               status.ctypes.data, C.addressof(stats))
+                               status.ctypes.data, C.addressof(stats), gray_cm[k + 1].data_ptr() if k < T else None)
     for k in range(1, W + 1):
         step_device(k)
         gather_poses(bt)

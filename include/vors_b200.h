@@ -160,6 +160,11 @@ int vors_batch_track_device(vors_batch* b, const double* depth_ts, const uint16_
                             const double* img_ts, const uint8_t* img_dev, int* status,
                             vors_track_stats* stats);
 /* n x Tracker::current_frame. */
+/* Device-resident variant of vors_batch_track_next: `next_img_dev` (or NULL) is the device buffer the next call will pass as
+ * `img_dev`; its copy into the frame pyramids and the pyramid build overlap this call's alignment. */
+int vors_batch_track_device_next(vors_batch* b, const double* depth_ts, const uint16_t* depth_dev,
+                                 const double* img_ts, const uint8_t* img_dev, const uint8_t* next_img_dev,
+                                 int* status, vors_track_stats* stats);
 int vors_batch_current_frames(const vors_batch* b, double* depth_ts, vors_pose* poses);
 int vors_batch_size(const vors_batch* b);
 /* Device time of the last track call's kernels, by stage (ms; CUDA events on the batch's stream):

@@ -558,6 +558,42 @@ def test_announced_next_frames_give_identical_results(vb):
     assert np.array_equal(plain, ann)
 
 
+def test_device_resident_path_and_its_announcements_match_the_host_path(vb):
+    """vors_batch_track_device (column-major device buffers) and vors_batch_track_device_next (next buffer announced) must give
+    bit-identical poses to the host-buffer path on the same frames."""
+    import ctypes as C
+
+    import torch
+
+    n, T = 4, 5
+    seqs = [synth.make_sequence(seed=950 + i, n_frames=T + 1, rows=60, cols=80, step_v=0.02, step_w=0.012) for i in range(n)]
+    cfg = vb.Config(nb_levels=3, **synth.scene_config_kwargs(seqs[0][0]))
+    frames = [np.ascontiguousarray(np.stack([s[1][k][0] for s in seqs])) for k in range(T + 1)]
+    depths = [np.ascontiguousarray(np.stack([s[1][k][1] for s in seqs])) for k in range(T + 1)]
+    dev = torch.device("cuda", 0)
+    gray_cm = [torch.from_numpy(f).to(dev).transpose(-1, -2).contiguous() for f in frames]
+    depth_cm = [torch.from_numpy(d.astype(np.int32)).to(dev).to(torch.uint16).transpose(-1, -2).contiguous() for d in depths]
+    torch.cuda.synchronize()
+
+    def run(mode):
+        bt = vb.BatchTracker(cfg, np.zeros(n), depths[0], np.zeros(n), frames[0])
+        for k in range(1, T + 1):
+            t = np.full(n, float(k))
+            if mode == "host":
+                status, _ = bt.track(t, depths[k], t, frames[k])
+                assert not status.any()
+            else:
+                status = np.zeros(n, np.int32)
+                nxt = gray_cm[k + 1].data_ptr() if (mode == "device_next" and k < T) else None
+                bt.track_device(t.ctypes.data, depth_cm[k].data_ptr(), t.ctypes.data, gray_cm[k].data_ptr(), status.ctypes.data, None, nxt)
+                assert not status.any()
+        return bt.current_frames()[1]
+
+    host = run("host")
+    assert np.array_equal(host, run("device"))
+    assert np.array_equal(host, run("device_next"))
+
+
 # ---- intrinsics variants: skew != 0 (general Jacobian kernel), negative fy (ICL-NUIM), full HD -------------------
 
 def _synth_pair_with_intrinsics(seed, rows, cols, **intr):

@@ -111,6 +111,7 @@ class Engine {
     uint8_t* d_stage8_alt = nullptr;
     AlignJob* d_jobs_alt = nullptr;  // job descriptors pointing into d_pyr_alt
     bool pending = false;            // d_pyr_alt holds prefetched frames
+    const uint8_t* pending_dev = nullptr;  // ... announced as a device buffer (else: the host pointers in pending_ptrs)
     std::vector<const uint8_t*> pending_ptrs;
     cudaEvent_t ev_pref{};
     uint16_t* d_stage16 = nullptr;   // row-major depth staging (launch order)
@@ -347,9 +348,10 @@ class Engine {
     }
     int upload_images_host(const uint8_t* const* img) { return upload_images_host_range(img, 0, n, L); }
 
-    int upload_images_device(const uint8_t* img_dev) {  // column-major, n*rows*cols contiguous
+    int upload_images_device(const uint8_t* img_dev, Launcher* X = nullptr, uint8_t* pyr_slab = nullptr) {  // column-major, n*rows*cols contiguous
         const size_t I = size_t(rows) * cols;
-        CU_TRY(cudaMemcpy2DAsync(d_pyr, size_t(g.pix_stride), img_dev, I, I, size_t(n), cudaMemcpyDeviceToDevice, L.stream));
+        CU_TRY(cudaMemcpy2DAsync(pyr_slab ? pyr_slab : d_pyr, size_t(g.pix_stride), img_dev, I, I, size_t(n), cudaMemcpyDeviceToDevice,
+                                 (X ? *X : L).stream));
         return VORS_OK;
     }
 
@@ -492,7 +494,7 @@ class Engine {
     // overlap this call's alignment.
     int track(const double* depth_ts, const uint16_t* const* depth, const uint16_t* depth_dev, const double* img_ts,
               const uint8_t* const* img, const uint8_t* img_dev, int* status, vors_track_stats* stats,
-              const uint8_t* const* next_img = nullptr) {
+              const uint8_t* const* next_img = nullptr, const uint8_t* next_img_dev = nullptr) {
         DEVICE_SCOPE(device);
         const unsigned long long launches0 = L.launches + LC.launches;
         int rc;
@@ -506,9 +508,10 @@ class Engine {
         // runs on the copy stream while the first half is being aligned (each half still fills the device: the align
         // kernel spreads every alignment over cap / (n/2) CTAs).  SURVEY §8f rank 2.
         // were these frames announced by the previous call?  Then they (and their pyramids) are already on the device.
-        bool prefetched = pending && !img_dev && img;
-        for (int i = 0; prefetched && i < n; ++i) prefetched = (img[i] == pending_ptrs[size_t(i)]);
+        bool prefetched = pending && (img_dev ? pending_dev == img_dev : (img && !pending_dev));
+        for (int i = 0; prefetched && !img_dev && i < n; ++i) prefetched = (img[i] == pending_ptrs[size_t(i)]);
         pending = false;
+        pending_dev = nullptr;
         if (prefetched) {
             std::swap(d_pyr, d_pyr_alt);
             std::swap(d_stage8, d_stage8_alt);
@@ -560,6 +563,12 @@ class Engine {
             launch_pyramid(LC, g, d_pyr_alt, nullptr, n);
             CU_TRY(cudaEventRecord(ev_pref, LC.stream));
             pending_ptrs.assign(next_img, next_img + n);
+            pending = true;
+        } else if (next_img_dev) {
+            if ((rc = upload_images_device(next_img_dev, &LC, d_pyr_alt)) != VORS_OK) return rc;
+            launch_pyramid(LC, g, d_pyr_alt, nullptr, n);
+            CU_TRY(cudaEventRecord(ev_pref, LC.stream));
+            pending_dev = next_img_dev;
             pending = true;
         }
         CU_TRY(cudaStreamSynchronize(L.stream));
@@ -805,6 +814,12 @@ int vors_batch_track_device(vors_batch* b, const double* depth_ts, const uint16_
                             const uint8_t* img_dev, int* status, vors_track_stats* stats) {
     if (!b || !depth_dev || !img_dev) return fail(VORS_E_INVALID, "null argument");
     return b->e->track(depth_ts, nullptr, depth_dev, img_ts, nullptr, img_dev, status, stats);
+}
+
+int vors_batch_track_device_next(vors_batch* b, const double* depth_ts, const uint16_t* depth_dev, const double* img_ts,
+                                 const uint8_t* img_dev, const uint8_t* next_img_dev, int* status, vors_track_stats* stats) {
+    if (!b || !depth_dev || !img_dev) return fail(VORS_E_INVALID, "null argument");
+    return b->e->track(depth_ts, nullptr, depth_dev, img_ts, nullptr, img_dev, status, stats, nullptr, next_img_dev);
 }
 
 int vors_batch_current_frames(const vors_batch* b, double* depth_ts, vors_pose* poses) {

@@ -101,6 +101,7 @@ SIGNATURES = {
     "vors_batch_track": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vors_batch_track_next": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vors_batch_track_device": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vors_batch_track_device_next": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vors_batch_current_frames": (C.c_int, [_vp, _vp, _vp]),
     "vors_batch_size": (C.c_int, [_vp]),
     "vors_batch_last_timing": (C.c_int, [_vp, _P(C.c_float)]),
@@ -314,8 +315,12 @@ class BatchTracker:
                                                           stats_ptr), True)
         return _check(self._lib.vors_batch_track(self._h, dts_ptr, depth_ptrs, its_ptr, img_ptrs, status_ptr, stats_ptr), True)
 
-    def track_device(self, dts_ptr, depth_dev_ptr, its_ptr, img_dev_ptr, status_ptr=None, stats_ptr=None):
-        """Device-resident column-major inputs ([n, cols, rows] memory order)."""
+    def track_device(self, dts_ptr, depth_dev_ptr, its_ptr, img_dev_ptr, status_ptr=None, stats_ptr=None, next_img_dev_ptr=None):
+        """Device-resident column-major inputs ([n, cols, rows] memory order).  `next_img_dev_ptr` announces the buffer of the
+        next call."""
+        if next_img_dev_ptr is not None:
+            return _check(self._lib.vors_batch_track_device_next(self._h, dts_ptr, depth_dev_ptr, its_ptr, img_dev_ptr, next_img_dev_ptr,
+                                                                 status_ptr, stats_ptr), True)
         return _check(self._lib.vors_batch_track_device(self._h, dts_ptr, depth_dev_ptr, its_ptr, img_dev_ptr, status_ptr,
                                                         stats_ptr), True)
 
