@@ -51,6 +51,10 @@ extern "C" {
 /* Replaces `track::Config` (src/core/track/inverse_compositional.rs:37-49) plus the constants the
  * reference hard-codes (src/core/track/lm_optimizer.rs:115,157,173,179,186; inverse_compositional.rs:224).
  * Always initialise with vors_config_default() (values of src/bin/vors_track.rs:34-40), then edit. */
+/* inverse_depth.rs:81-98 `strategy_dso_mean` (Tracker default) / :105-152 `strategy_statistically_similar` (values whose
+ * squared distance to the fused inverse depth reaches the fused variance discard the bloc; a discarded bloc is not a candidate) */
+enum { VORS_FUSION_DSO_MEAN = 0, VORS_FUSION_STATISTICALLY_SIMILAR = 1 };
+
 typedef struct vors_config {
     uint32_t nb_levels;                 /* Config::nb_levels */
     uint32_t candidates_diff_threshold; /* Config::candidates_diff_threshold (u16 range) */
@@ -69,7 +73,9 @@ typedef struct vors_config {
     int32_t device;                /* CUDA ordinal; -1 = current device */
     uint32_t team_size;            /* CTAs cooperating on one alignment; 0 = auto */
     uint32_t dso_nb_target;        /* VORS_CANDIDATES_DSO: target number of level-0 candidates (2000) */
-    uint32_t reserved[3];
+    uint32_t idepth_fusion;        /* VORS_FUSION_*: how 2x2 blocs of inverse depths merge up the pyramid (multires::halve with
+                                      inverse_depth::fuse); 0 = strategy_dso_mean, what the Tracker uses (inverse_compositional.rs:135-138) */
+    uint32_t reserved[2];
 } vors_config;
 
 /* Replaces `Iso3 = Isometry3<f32>` (src/misc/type_aliases.rs:30); printed by the reference as

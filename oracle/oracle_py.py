@@ -36,7 +36,8 @@ class Config(C.Structure):
         ("device", C.c_int32),
         ("team_size", C.c_uint32),
         ("dso_nb_target", C.c_uint32),
-        ("reserved", C.c_uint32 * 3),
+        ("idepth_fusion", C.c_uint32),
+        ("reserved", C.c_uint32 * 2),
     ]
 
 

@@ -252,6 +252,52 @@ inline IDepth fuse_dso_mean(IDepth a, IDepth b, IDepth c, IDepth d) {
     return r;
 }
 
+// inverse_depth.rs:105-152 `strategy_statistically_similar` behind `fuse`: the known children merge only if every one of
+// them lies within one (fused) standard deviation of the fused value; otherwise the bloc is Discarded (kind 1), which
+// every consumer treats like Unknown (`with_variance`, :68-74; `extract_z`, inverse_compositional.rs:270-276).
+inline IDepth fuse_statistically_similar(IDepth a, IDepth b, IDepth c, IDepth d) {
+    Float ds[4], vs[4];
+    int n = 0;
+    for (const IDepth* p : {&a, &b, &c, &d})
+        if (p->kind == 2) {
+            ds[n] = p->d;
+            vs[n] = p->v;
+            ++n;
+        }
+    IDepth r;
+    Float new_d = 0, new_v = 0;
+    switch (n) {
+        case 1: r.kind = 2; r.d = ds[0]; r.v = 2.0f * vs[0]; return r;
+        case 2: new_d = (ds[0] * vs[1] + ds[1] * vs[0]) / (vs[0] + vs[1]);
+                new_v = (vs[0] + vs[1]) / 2.0f;
+                break;
+        case 3: { const Float v12 = vs[0] * vs[1], v13 = vs[0] * vs[2], v23 = vs[1] * vs[2];
+                  new_d = (ds[0] * v23 + ds[1] * v13 + ds[2] * v12) / (v12 + v13 + v23);
+                  new_v = 2.0f * (vs[0] + vs[1] + vs[2]) / 9.0f;
+                  break; }
+        case 4: { const Float v123 = vs[0] * vs[1] * vs[2], v234 = vs[1] * vs[2] * vs[3], v341 = vs[2] * vs[3] * vs[0],
+                              v412 = vs[3] * vs[0] * vs[1];
+                  const Float sum = v123 + v234 + v341 + v412;
+                  new_d = (ds[0] * v234 + ds[1] * v341 + ds[2] * v412 + ds[3] * v123) / sum;
+                  new_v = (vs[0] + vs[1] + vs[2] + vs[3]) / 8.0f;
+                  break; }
+        default: return r;
+    }
+    bool similar = true;
+    for (int k = 0; k < n; ++k) {
+        const Float e = ds[k] - new_d;
+        similar = similar && (e * e < new_v);
+    }
+    if (similar) {
+        r.kind = 2;
+        r.d = new_d;
+        r.v = new_v;
+    } else {
+        r.kind = 1;
+    }
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------
 // camera.rs:84-140 `Intrinsics`.
 struct Intrinsics {
@@ -587,9 +633,10 @@ std::unique_ptr<Keyframe> precompute_multires_data(const ref_config& cfg, const 
     Mat<IDepth> id0(depth.rows, depth.cols);
     for (size_t k = 0; k < id0.size(); ++k)
         id0.d[k] = mask0.d[k] ? from_depth(cfg.depth_scale, depth.d[k], cfg.idepth_variance) : IDepth{};
-    // :135-138 idepth pyramid with fuse(strategy_dso_mean)
-    auto idepth_multires = limited_sequence(int(cfg.nb_levels), std::move(id0), [](const Mat<IDepth>& m, Mat<IDepth>& o) {
-        return halve<IDepth, IDepth>(m, fuse_dso_mean, o);
+    // :135-138 idepth pyramid with fuse(strategy_dso_mean); the other strategy the reference ships is selectable
+    const bool similar = cfg.idepth_fusion == 1;
+    auto idepth_multires = limited_sequence(int(cfg.nb_levels), std::move(id0), [similar](const Mat<IDepth>& m, Mat<IDepth>& o) {
+        return similar ? halve<IDepth, IDepth>(m, fuse_statistically_similar, o) : halve<IDepth, IDepth>(m, fuse_dso_mean, o);
     });
 
     const size_t L = idepth_multires.size();

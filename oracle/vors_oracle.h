@@ -56,7 +56,8 @@ typedef struct ref_config {
     int32_t device;     /* unused by the oracle */
     uint32_t team_size; /* unused by the oracle */
     uint32_t dso_nb_target;
-    uint32_t reserved[3];
+    uint32_t idepth_fusion; /* 0 strategy_dso_mean (Tracker), 1 strategy_statistically_similar (inverse_depth.rs:105-152) */
+    uint32_t reserved[2];
 } ref_config;
 
 typedef struct ref_pose {

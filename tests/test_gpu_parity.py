@@ -558,6 +558,39 @@ def test_announced_next_frames_give_identical_results(vb):
     assert np.array_equal(plain, ann)
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_statistically_similar_fusion_option(vb, oracle, mode):
+    """idepth_fusion = 1 (inverse_depth.rs:105-152): inverse-depth pyramid and candidate lists bit-identical to the oracle,
+    tracked pose within tolerance, on a scene with a depth hole and a depth step (discarded blocs)."""
+    scene, frames, _ = synth.make_sequence(seed=55, n_frames=3, rows=120, cols=160, step_v=0.01, step_w=0.006)
+    def spoil(d):
+        d = d.copy()
+        d[10:31, 20:51] = 0
+        d[60:, 81:] = (d[60:, 81:].astype(np.float32) * 1.6).astype(np.uint16)
+        return d
+    depth0 = spoil(frames[0][1])
+    cfg, ocfg = _cfgs(vb, oracle, scene, nb_levels=4, candidate_mode=mode, idepth_fusion=1)
+    kf, okf = vb.Keyframe(cfg, depth0, frames[0][0]), oracle.Keyframe(ocfg, depth0, frames[0][0])
+    discarded = 0
+    for l in range(4):
+        d, _ = okf.idepth_map(l)
+        got = kf.idepth_map(l)
+        assert np.array_equal(np.isnan(got), np.isnan(d))
+        assert np.array_equal(got[~np.isnan(d)], d[~np.isnan(d)])
+        assert kf.n_points(l) == okf.n_points(l)
+        assert np.array_equal(kf.points(l)[0], okf.points(l)[0])
+    d1, _ = okf.idepth_map(1)
+    d1_mean, _ = oracle.Keyframe(_cfgs(vb, oracle, scene, nb_levels=4, candidate_mode=mode)[1], depth0, frames[0][0]).idepth_map(1)
+    assert np.isnan(d1).sum() > np.isnan(d1_mean).sum()  # the depth step did discard blocs
+    t = cfg.init(0.0, depth0, 0.0, frames[0][0])
+    ot = oracle.Tracker(ocfg, 0.0, depth0, 0.0, frames[0][0])
+    for k in (1, 2):
+        st = t.track(float(k), spoil(frames[k][1]), float(k), frames[k][0])
+        ost = ot.track(float(k), spoil(frames[k][1]), float(k), frames[k][0])
+        assert st.status == ost[1].status
+    _pose_close(t.current_frame()[1].as_array(), ot.current_frame()[1].as_array(), oracle)
+
+
 def test_device_resident_path_and_its_announcements_match_the_host_path(vb):
     """vors_batch_track_device (column-major device buffers) and vors_batch_track_device_next (next buffer announced) must give
     bit-identical poses to the host-buffer path on the same frames."""

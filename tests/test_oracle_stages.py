@@ -133,6 +133,62 @@ def test_idepth_pyramid_and_extract_order(oracle, small_pair):
         assert np.array_equal(idepth, dl[rows, cols])
 
 
+def _similar_numpy(ds, vs):
+    """inverse_depth.rs:105-152 restated independently (f32, the reference's operation order); returns (d, v) or None."""
+    f = np.float32
+    ds, vs = [f(x) for x in ds], [f(x) for x in vs]
+    n = len(ds)
+    if n == 1:
+        return ds[0], f(2.0) * vs[0]
+    if n == 2:
+        nd = (ds[0] * vs[1] + ds[1] * vs[0]) / (vs[0] + vs[1])
+        nv = (vs[0] + vs[1]) / f(2.0)
+    elif n == 3:
+        v12, v13, v23 = vs[0] * vs[1], vs[0] * vs[2], vs[1] * vs[2]
+        nd = (ds[0] * v23 + ds[1] * v13 + ds[2] * v12) / (v12 + v13 + v23)
+        nv = f(2.0) * (vs[0] + vs[1] + vs[2]) / f(9.0)
+    else:
+        v123, v234, v341, v412 = vs[0] * vs[1] * vs[2], vs[1] * vs[2] * vs[3], vs[2] * vs[3] * vs[0], vs[3] * vs[0] * vs[1]
+        nd = (ds[0] * v234 + ds[1] * v341 + ds[2] * v412 + ds[3] * v123) / (v123 + v234 + v341 + v412)
+        nv = (vs[0] + vs[1] + vs[2] + vs[3]) / f(8.0)
+    return (nd, nv) if all((d - nd) * (d - nd) < nv for d in ds) else None
+
+
+def test_statistically_similar_fusion_matches_independent_restatement(oracle, small_pair):
+    """The reference's other fusion strategy (inverse_depth.rs:105-152), selectable with idepth_fusion = 1: a bloc whose known
+    children disagree by more than one fused standard deviation is Discarded (not a candidate).  Checked bloc by bloc against
+    a numpy restatement on a scene with a depth hole and a depth step (so that 1-, 2-, 3-, 4-child and discarded blocs occur)."""
+    scene, f0, _, _ = small_pair
+    depth = f0[1].copy()
+    depth[10:31, 20:51] = 0                                    # hole with odd borders: 2- and 3-child blocs
+    depth[40, 100] = depth[40, 101] = depth[41, 100] = 0       # a bloc with a single known child
+    depth[60:, 81:] = (depth[60:, 81:].astype(np.float32) * 1.6).astype(np.uint16)  # depth step: dissimilar blocs
+    cfg = _cfg(oracle, scene, nb_levels=4, candidate_mode=1, idepth_fusion=1, idepth_variance=1e-4)
+    kf = oracle.Keyframe(cfg, depth, f0[0])
+    seen = {1: 0, 2: 0, 3: 0, 4: 0, "discarded": 0}
+    for l in range(1, 4):
+        dl, wl = kf.idepth_map(l)
+        dp, wp = kf.idepth_map(l - 1)
+        for r in range(dl.shape[0]):
+            for c in range(dl.shape[1]):
+                kids = [(dp[2 * r + dr, 2 * c + dc], wp[2 * r + dr, 2 * c + dc]) for dc, dr in ((0, 0), (0, 1), (1, 0), (1, 1))]  # a, b, c, d
+                kids = [k for k in kids if not np.isnan(k[0])]
+                if not kids:
+                    assert np.isnan(dl[r, c])
+                    continue
+                want = _similar_numpy([k[0] for k in kids], [k[1] for k in kids])
+                if want is None:
+                    assert np.isnan(dl[r, c]) and wl[r, c] == 0
+                    seen["discarded"] += 1
+                else:
+                    assert dl[r, c] == want[0] and wl[r, c] == want[1], (l, r, c)
+                    seen[len(kids)] += 1
+    assert all(v > 0 for v in seen.values()), seen
+    # dso_mean (the Tracker's strategy) never discards: more candidates above level 0
+    kf0 = oracle.Keyframe(_cfg(oracle, scene, nb_levels=4, candidate_mode=1), depth, f0[0])
+    assert kf.n_points(1) < kf0.n_points(1)
+
+
 def test_jacobian_matches_finite_differences_of_warp(oracle, small_pair):
     """J = grad(T) . d(warp)/d(xi) at xi = 0 (inverse_compositional.rs:313-341): check the geometric part
     against central differences of lm_optimizer.rs:213-219's warp composed with se3::exp."""

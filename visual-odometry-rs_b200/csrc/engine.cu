@@ -196,6 +196,7 @@ class Engine {
             (void)cudaGetLastError();
             return fail(VORS_E_CUDA, "no CUDA device available (libvors_b200 has no CPU fallback)");
         }
+        if (cfg.idepth_fusion > VORS_FUSION_STATISTICALLY_SIMILAR) return fail(VORS_E_INVALID, "unknown idepth_fusion");
         if (cfg.device >= 0) {
             if (cfg.device >= count) return fail(VORS_E_INVALID, "device ordinal out of range");
             device = cfg.device;
@@ -390,7 +391,8 @@ class Engine {
             launch_c2f(L, g, uint16_t(cfg.candidates_diff_threshold), d_g2, d_mask, d_items, m);
         }
         // a 1-level coarse-to-fine pyramid selects every pixel (coarse_to_fine.rs:19-21)
-        launch_idepth(L, g, depth_slab, size_t(rows) * cols, d_mask, dense || (g.L == 1 && !dso), cfg.depth_scale, cfg.idepth_variance, d_idepth,
+        launch_idepth(L, g, depth_slab, size_t(rows) * cols, d_mask, dense || (g.L == 1 && !dso), cfg.depth_scale, cfg.idepth_variance,
+                      cfg.idepth_fusion == VORS_FUSION_STATISTICALLY_SIMILAR ? 1 : 0, d_idepth,
                       d_weight, d_items, m);
         launch_compact(L, g, d_idepth, d_pyr, d_grad, d_blk_count, d_n_points, d_pts, d_items, m);
         launch_h_total(L, g, intr, d_pts, d_n_points, d_h_total, d_items, m);

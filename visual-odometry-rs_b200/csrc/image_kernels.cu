@@ -199,7 +199,9 @@ __global__ void k_idepth0(const Geom g, const uint16_t* __restrict__ depth_slab,
 // Row G: one halving of the idepth pyramid with inverse_depth::fuse + strategy_dso_mean
 // (inverse_depth.rs:49-98): weighted mean of the known children in (a,b,c,d) order, evaluated left
 // to right in f32; one known child is copied verbatim; none -> Unknown.
-__global__ void k_idepth_halve(const Geom g, int l, float* __restrict__ idepth_slab, float* __restrict__ weight_slab,
+// `similar` selects inverse_depth.rs:105-152 `strategy_statistically_similar` instead: the known children merge only if each
+// lies within one fused standard deviation of the fused value, else the bloc is Discarded (stored like Unknown: NaN).
+__global__ void k_idepth_halve(const Geom g, int l, int similar, float* __restrict__ idepth_slab, float* __restrict__ weight_slab,
                                const int* __restrict__ items) {
     const size_t base = size_t(item_of(items, blockIdx.y)) * g.pix_stride;
     const float* din = idepth_slab + base + g.off[l - 1];
@@ -223,7 +225,40 @@ __global__ void k_idepth_halve(const Geom g, int l, float* __restrict__ idepth_s
             }
         float d = __int_as_float(0x7fc00000), w = 0.0f;
         // explicit __fmul_rn/__fadd_rn: the reference rounds every product and sum (no FMA contraction)
-        if (n == 1) {
+        if (similar) {
+            float nd = 0.0f, nv = 0.0f;
+            if (n == 1) {
+                d = ds[0];
+                w = __fmul_rn(2.0f, vs[0]);
+            } else if (n == 2) {
+                nd = __fdiv_rn(__fadd_rn(__fmul_rn(ds[0], vs[1]), __fmul_rn(ds[1], vs[0])), __fadd_rn(vs[0], vs[1]));
+                nv = __fdiv_rn(__fadd_rn(vs[0], vs[1]), 2.0f);
+            } else if (n == 3) {
+                const float v12 = __fmul_rn(vs[0], vs[1]), v13 = __fmul_rn(vs[0], vs[2]), v23 = __fmul_rn(vs[1], vs[2]);
+                nd = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(ds[0], v23), __fmul_rn(ds[1], v13)), __fmul_rn(ds[2], v12)),
+                               __fadd_rn(__fadd_rn(v12, v13), v23));
+                nv = __fdiv_rn(__fmul_rn(2.0f, __fadd_rn(__fadd_rn(vs[0], vs[1]), vs[2])), 9.0f);
+            } else if (n == 4) {
+                const float v123 = __fmul_rn(__fmul_rn(vs[0], vs[1]), vs[2]), v234 = __fmul_rn(__fmul_rn(vs[1], vs[2]), vs[3]);
+                const float v341 = __fmul_rn(__fmul_rn(vs[2], vs[3]), vs[0]), v412 = __fmul_rn(__fmul_rn(vs[3], vs[0]), vs[1]);
+                const float sum = __fadd_rn(__fadd_rn(__fadd_rn(v123, v234), v341), v412);
+                nd = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(ds[0], v234), __fmul_rn(ds[1], v341)), __fmul_rn(ds[2], v412)),
+                                         __fmul_rn(ds[3], v123)),
+                               sum);
+                nv = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(vs[0], vs[1]), vs[2]), vs[3]), 8.0f);
+            }
+            if (n >= 2) {
+                bool ok = true;
+                for (int k = 0; k < n; ++k) {
+                    const float e = __fsub_rn(ds[k], nd);
+                    ok = ok && (__fmul_rn(e, e) < nv);
+                }
+                if (ok) {
+                    d = nd;
+                    w = nv;
+                }
+            }
+        } else if (n == 1) {
             d = ds[0];
             w = vs[0];
         } else if (n == 2) {
@@ -501,7 +536,7 @@ void launch_c2f(Launcher& L, const Geom& g, uint16_t thresh, const uint16_t* g2_
     }
 }
 void launch_idepth(Launcher& L, const Geom& g, const uint16_t* depth_slab, size_t depth_stride, const uint8_t* mask_slab, int dense,
-                   float scale, float variance, float* idepth_slab, float* weight_slab, const int* items, int m) {
+                   float scale, float variance, int similar, float* idepth_slab, float* weight_slab, const int* items, int m) {
     {
         dim3 grid(grid_for(g.rows[0] * g.cols[0], 256), m);
         k_idepth0<<<grid, 256, 0, L.stream>>>(g, depth_slab, depth_stride, mask_slab, dense, scale, variance, idepth_slab,
@@ -510,7 +545,7 @@ void launch_idepth(Launcher& L, const Geom& g, const uint16_t* depth_slab, size_
     }
     for (int l = 1; l < g.L; ++l) {
         dim3 grid(grid_for(g.rows[l] * g.cols[l], 256), m);
-        k_idepth_halve<<<grid, 256, 0, L.stream>>>(g, l, idepth_slab, weight_slab, items);
+        k_idepth_halve<<<grid, 256, 0, L.stream>>>(g, l, similar, idepth_slab, weight_slab, items);
         ++L.launches;
     }
 }

@@ -177,7 +177,8 @@ void launch_gradients(Launcher& L, const Geom& g, const uint8_t* pyr_slab, uint3
 void launch_c2f(Launcher& L, const Geom& g, uint16_t thresh, const uint16_t* g2_slab, uint8_t* mask_slab, const int* items,
                 int m);
 void launch_idepth(Launcher& L, const Geom& g, const uint16_t* depth_slab, size_t depth_stride, const uint8_t* mask_slab,
-                   int dense, float scale, float variance, float* idepth_slab, float* weight_slab, const int* items, int m);
+                   int dense, float scale, float variance, int similar, float* idepth_slab, float* weight_slab, const int* items,
+                   int m);
 void launch_compact(Launcher& L, const Geom& g, const float* idepth_slab, const uint8_t* pyr_slab, const uint32_t* grad_slab,
                     int* blk_count, int* n_points, uint32_t* pts_slab, const int* items, int m);
 void launch_h_total(Launcher& L, const Geom& g, const Intrinsics* intr, const uint32_t* pts_slab, const int* n_points,

@@ -50,7 +50,8 @@ class ConfigStruct(C.Structure):
         ("device", C.c_int32),
         ("team_size", C.c_uint32),
         ("dso_nb_target", C.c_uint32),
-        ("reserved", C.c_uint32 * 3),
+        ("idepth_fusion", C.c_uint32),
+        ("reserved", C.c_uint32 * 2),
     ]
 
 
