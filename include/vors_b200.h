@@ -75,7 +75,11 @@ typedef struct vors_config {
     uint32_t dso_nb_target;        /* VORS_CANDIDATES_DSO: target number of level-0 candidates (2000) */
     uint32_t idepth_fusion;        /* VORS_FUSION_*: how 2x2 blocs of inverse depths merge up the pyramid (multires::halve with
                                       inverse_depth::fuse); 0 = strategy_dso_mean, what the Tracker uses (inverse_compositional.rs:135-138) */
-    uint32_t reserved[2];
+    float huber_delta;             /* > 0: Huber-weighted residuals (the north_star's extra; the reference has no robust weighting,
+                                      lm_optimizer.rs:94-100): energy = mean rho_delta(r), g = sum w J r, H = sum w J J^T with
+                                      w = min(1, delta / |r|) (grey levels).  0 = the reference's plain L2.  Excluded from parity
+                                      with the reference; checked against the oracle's same option. */
+    uint32_t reserved[1];
 } vors_config;
 
 /* Replaces `Iso3 = Isometry3<f32>` (src/misc/type_aliases.rs:30); printed by the reference as

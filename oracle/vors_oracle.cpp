@@ -598,7 +598,18 @@ struct Keyframe {
     std::vector<std::vector<std::array<Float, 36>>> hes;  // full 6x6 per point, like the reference
     std::vector<Mat<IDepth>> idepth_maps;
     Mat<uint8_t> mask0;
+    Float huber_delta = 0.0f;  // extension (not in the reference): > 0 switches eval_energy / compute_eval_data to Huber weights
 };
+
+// Huber loss rho(r) (r^2 inside |r| <= delta, delta (2|r| - delta) outside) and its IRLS weight min(1, delta / |r|).
+inline Float huber_rho(Float r, Float delta) {
+    const Float ar = std::fabs(r);
+    return ar <= delta ? r * r : delta * (2.0f * ar - delta);
+}
+inline Float huber_weight(Float r, Float delta) {
+    const Float ar = std::fabs(r);
+    return ar <= delta ? 1.0f : delta / ar;
+}
 
 int dso_select_impl(const Mat<uint16_t>& gradients, int nb_target, int nb_iterations_left, uint64_t seed,
                     Mat<uint8_t>& mask, int* used_random);
@@ -608,6 +619,7 @@ std::unique_ptr<Keyframe> precompute_multires_data(const ref_config& cfg, const 
                                                    std::vector<Intrinsics> intrinsics,
                                                    std::vector<Mat<uint8_t>> img_multires) {
     auto kf = std::make_unique<Keyframe>();
+    kf->huber_delta = cfg.huber_delta;
     std::vector<Mat<int16_t>> gxs, gys;
     std::vector<Mat<uint16_t>> g2s;
     gradients_tracker(img_multires, gxs, gys, g2s);
@@ -706,8 +718,9 @@ Precomputed eval_energy(const Keyframe& kf, int lvl, const uint8_t* image, int r
         warp(model, Float(x), Float(y), zs[idx], k, u, v);
         if (interpolate(u, v, image, rows, cols, im)) {
             const Float r = im - Float(tmpl(int(y), int(x)));
-            energy_sum += r * r;
-            energy_sum64 += double(r) * double(r);
+            const Float e = kf.huber_delta > 0.0f ? huber_rho(r, kf.huber_delta) : r * r;
+            energy_sum += e;
+            energy_sum64 += kf.huber_delta > 0.0f ? double(e) : double(r) * double(r);
             pre.residuals.push_back(r);
             pre.inside_indices.push_back(uint32_t(idx));
         }
@@ -725,10 +738,11 @@ EvalData compute_eval_data(const Keyframe& kf, int lvl, const Iso& model, const 
         double gd[6] = {0}, Hd[36] = {0};
         for (size_t i = 0; i < pre.inside_indices.size(); ++i) {
             const auto& jac = kf.jac[lvl][pre.inside_indices[i]];
-            const double r = pre.residuals[i];
+            const double w = kf.huber_delta > 0.0f ? double(huber_weight(pre.residuals[i], kf.huber_delta)) : 1.0;
+            const double r = w * double(pre.residuals[i]);
             for (int a = 0; a < 6; ++a) gd[a] += double(jac[a]) * r;
             for (int a = 0; a < 6; ++a)
-                for (int b = 0; b < 6; ++b) Hd[a * 6 + b] += double(jac[a]) * double(jac[b]);
+                for (int b = 0; b < 6; ++b) Hd[a * 6 + b] += w * double(jac[a]) * double(jac[b]);
         }
         for (int a = 0; a < 6; ++a) e.gradient[a] = Float(gd[a]);
         for (int a = 0; a < 6; ++a)
@@ -741,10 +755,16 @@ EvalData compute_eval_data(const Keyframe& kf, int lvl, const Iso& model, const 
         const uint32_t idx = pre.inside_indices[i];
         const auto& jac = kf.jac[lvl][idx];
         const auto& hes = kf.hes[lvl][idx];
-        const Float r = pre.residuals[i];
+        const Float w = kf.huber_delta > 0.0f ? huber_weight(pre.residuals[i], kf.huber_delta) : 1.0f;
+        const Float r = kf.huber_delta > 0.0f ? w * pre.residuals[i] : pre.residuals[i];
         for (int a = 0; a < 6; ++a) e.gradient[a] += jac[a] * r;
-        for (int a = 0; a < 6; ++a)
-            for (int b = 0; b < 6; ++b) e.hessian.m[a][b] += hes[a * 6 + b];
+        if (kf.huber_delta > 0.0f) {
+            for (int a = 0; a < 6; ++a)
+                for (int b = 0; b < 6; ++b) e.hessian.m[a][b] += w * hes[a * 6 + b];
+        } else {
+            for (int a = 0; a < 6; ++a)
+                for (int b = 0; b < 6; ++b) e.hessian.m[a][b] += hes[a * 6 + b];
+        }
     }
     e.energy = pre.energy;
     e.model = model;
@@ -1207,12 +1227,14 @@ int ref_eval(const ref_keyframe* kf, int level, const uint8_t* image, int rows, 
         double es = 0, gd[6] = {0}, Hd[36] = {0};
         for (size_t i = 0; i < pre.inside_indices.size(); ++i) {
             const uint32_t idx = pre.inside_indices[i];
-            const double r = pre.residuals[i];
-            es += r * r;
+            const Float hd = kf->k->huber_delta;
+            const double w = hd > 0.0f ? double(huber_weight(pre.residuals[i], hd)) : 1.0;
+            es += hd > 0.0f ? double(huber_rho(pre.residuals[i], hd)) : double(pre.residuals[i]) * double(pre.residuals[i]);
+            const double r = w * double(pre.residuals[i]);
             const auto& J = kf->k->jac[level][idx];
             for (int a = 0; a < 6; ++a) gd[a] += double(J[a]) * r;
             for (int a = 0; a < 6; ++a)
-                for (int b = 0; b < 6; ++b) Hd[a * 6 + b] += double(J[a]) * double(J[b]);
+                for (int b = 0; b < 6; ++b) Hd[a * 6 + b] += w * double(J[a]) * double(J[b]);
         }
         *energy = float(es / double(pre.residuals.size()));
         for (int a = 0; a < 6; ++a) g[a] = float(gd[a]);

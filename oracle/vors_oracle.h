@@ -57,7 +57,8 @@ typedef struct ref_config {
     uint32_t team_size; /* unused by the oracle */
     uint32_t dso_nb_target;
     uint32_t idepth_fusion; /* 0 strategy_dso_mean (Tracker), 1 strategy_statistically_similar (inverse_depth.rs:105-152) */
-    uint32_t reserved[2];
+    float huber_delta;      /* > 0: Huber weights (extension, not in the reference); 0 = plain L2 like the reference */
+    uint32_t reserved[1];
 } ref_config;
 
 typedef struct ref_pose {

@@ -591,6 +591,41 @@ def test_statistically_similar_fusion_option(vb, oracle, mode):
     _pose_close(t.current_frame()[1].as_array(), ot.current_frame()[1].as_array(), oracle)
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("skew", [0.0, 0.4])
+def test_huber_option_matches_oracle(vb, oracle, mode, skew):
+    """huber_delta > 0 (the north_star's extra; the reference itself is plain L2, lm_optimizer.rs:94-100): energy = mean Huber loss,
+    g = sum w J r, H = sum w J J^T summed directly.  One pass and the tracked pose against the oracle's same option, on frames
+    with an occluder so that many residuals are in the linear part of the loss."""
+    scene, frames, _ = synth.make_sequence(seed=66, n_frames=3, rows=120, cols=160, step_v=0.01, step_w=0.006)
+    def occlude(g):
+        g = g.copy()
+        g[30:60, 50:90] = 255 - g[30:60, 50:90]
+        return g
+    kw = dict(nb_levels=3, candidate_mode=mode, huber_delta=6.0, skew=skew)
+    cfg, ocfg = _cfgs(vb, oracle, scene, **kw)
+    kf, okf = vb.Keyframe(cfg, frames[0][1], frames[0][0]), oracle.Keyframe(ocfg, frames[0][1], frames[0][0])
+    pyr1 = oracle.mean_pyramid(occlude(frames[1][0]), 3)
+    m = oracle.se3_exp([0.003, -0.002, 0.002, 0.001, 0.002, -0.001])
+    for l in (2, 0):
+        e, n, g, H = kf.align_pass(l, pyr1[l], vb.Pose.from_arrays(m.t, m.q))
+        e64, n64, g64, H64 = okf.eval(l, pyr1[l], m, 1)
+        assert n == n64
+        assert abs(e - e64) <= 1e-5 * abs(e64)
+        assert np.all(np.abs(g - g64) <= 5e-5 * np.abs(g64).max() + 1e-3)
+        assert np.all(np.abs(H - H64) <= 1e-5 * np.abs(H64).max())
+        # and it is not the L2 energy: the occluder's residuals are down-weighted
+        e_l2 = oracle.Keyframe(_cfgs(vb, oracle, scene, nb_levels=3, candidate_mode=mode, skew=skew)[1], frames[0][1], frames[0][0]).eval(l, pyr1[l], m, 1)[0]
+        assert e64 < 0.8 * e_l2
+    t = cfg.init(0.0, frames[0][1], 0.0, frames[0][0])
+    ot = oracle.Tracker(ocfg, 0.0, frames[0][1], 0.0, frames[0][0])
+    for k in (1, 2):
+        st = t.track(float(k), frames[k][1], float(k), occlude(frames[k][0]))
+        ost = ot.track(float(k), frames[k][1], float(k), occlude(frames[k][0]))
+        assert st.status == ost[1].status == 0
+    _pose_close(t.current_frame()[1].as_array(), ot.current_frame()[1].as_array(), oracle)
+
+
 def test_device_resident_path_and_its_announcements_match_the_host_path(vb):
     """vors_batch_track_device (column-major device buffers) and vors_batch_track_device_next (next buffer announced) must give
     bit-identical poses to the host-buffer path on the same frames."""

@@ -189,6 +189,28 @@ def test_statistically_similar_fusion_matches_independent_restatement(oracle, sm
     assert kf.n_points(1) < kf0.n_points(1)
 
 
+def test_huber_option_of_the_oracle(oracle, small_pair):
+    """huber_delta (an extension; the reference is plain L2): a huge delta reproduces the L2 evaluation exactly, a small
+    one lowers the energy and shrinks g and H (weights <= 1), and H stays symmetric; the default is L2."""
+    scene, f0, f1, _ = small_pair
+    img1 = f1[0].copy()
+    img1[30:60, 50:90] = 255 - img1[30:60, 50:90]  # occluder: large residuals
+    m = oracle.se3_exp([0.003, -0.002, 0.002, 0.001, 0.002, -0.001])
+    out = {}
+    for hd in (0.0, 1e9, 6.0):
+        kf = oracle.Keyframe(_cfg(oracle, scene, nb_levels=3, huber_delta=hd), f0[1], f0[0])
+        out[hd] = [kf.eval(0, img1, m, acc) for acc in (0, 1)]
+    assert oracle.default_config().huber_delta == 0.0
+    for acc in (0, 1):
+        e0, n0, g0, H0 = out[0.0][acc]
+        e9, n9, g9, H9 = out[1e9][acc]
+        e6, n6, g6, H6 = out[6.0][acc]
+        assert n0 == n9 == n6
+        assert e0 == e9 and np.array_equal(g0, g9) and np.array_equal(H0, H9)
+        assert e6 < 0.8 * e0
+        assert np.all(np.diag(H6) < np.diag(H0)) and np.allclose(H6, H6.T, rtol=1e-6)
+
+
 def test_jacobian_matches_finite_differences_of_warp(oracle, small_pair):
     """J = grad(T) . d(warp)/d(xi) at xi = 0 (inverse_compositional.rs:313-341): check the geometric part
     against central differences of lm_optimizer.rs:213-219's warp composed with se3::exp."""

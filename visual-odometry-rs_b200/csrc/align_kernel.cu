@@ -84,7 +84,7 @@ struct LmShared {
     int n_passes;
     int trace_len;
     unsigned long long point_passes;
-    float warp_part[kWarps][16];   // per-warp sums of the pass accumulators (E, n, 11 moments or 6 gradient entries)
+    float warp_part[kWarps][32];   // per-warp sums of the pass accumulators (E, n, 11 moments / g[6] / Huber: g[6] and H[21])
     double hout[kWarps][21];       // per-warp sum of J J^T over the candidates outside for sure, cumulative over a level's passes
     double hout_pass[kWarps][21];  // per-warp sum of J J^T over this pass's deferred candidates that turned out outside
     double h_total[21];            // the level's H_total (k_h_total), cached for the per-pass serial part
@@ -157,13 +157,16 @@ __device__ __host__ constexpr int tri(int a, int b) { return a * 6 - a * (a - 1)
 // six Jacobian entries, eleven moments of (p, q) = (gu r, gv r) from which g = sum J r is assembled once per pass
 // in f64 (J is linear in (gu, gv) with coefficients polynomial in a = x - cu, b = y - cv and idepth,
 // inverse_compositional.rs:326-340) - 16 instead of 29 instructions per candidate.  With skew the plain g[6].
+// kHuber (extension, vors_config.huber_delta > 0): the weights depend on the residual, so neither the moments nor
+// H = H_total - H_outside apply; g[6] and the 21 entries of H are summed directly (s[0..5], s[6..26]).
+template <bool kHuber>
 struct Acc {
     float e;
-    float s[11];
+    float s[kHuber ? 27 : 11];
 };
 enum { kSrp, kSrq, kSrt, kSabp, kSbbq, kSq, kSaap, kSp, kSabq, kSbp, kSaq };
 
-__device__ __forceinline__ void accumulate_moments(Acc& acc, float gu, float gv, float a, float b, float rho, float r) {
+__device__ __forceinline__ void accumulate_moments(Acc<false>& acc, float gu, float gv, float a, float b, float rho, float r) {
     const float p = gu * r, q = gv * r;
     const float ap = a * p, bq = b * q;
     acc.s[kSrp] = fmaf(rho, p, acc.s[kSrp]);
@@ -177,6 +180,23 @@ __device__ __forceinline__ void accumulate_moments(Acc& acc, float gu, float gv,
     acc.s[kSq] += q;
     acc.s[kSbp] = fmaf(b, p, acc.s[kSbp]);
     acc.s[kSaq] = fmaf(a, q, acc.s[kSaq]);
+}
+
+// Huber-weighted contribution of one inside candidate: rho_delta(r) to the energy, w J r to g, w J J^T to H.
+__device__ __forceinline__ void accumulate_huber(Acc<true>& acc, const float (&J)[6], float r, float delta) {
+    const float ar = fabsf(r);
+    const bool quad = ar <= delta;
+    const float w = quad ? 1.0f : delta / ar;
+    acc.e += quad ? r * r : delta * (2.0f * ar - delta);
+    const float wr = w * r;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc.s[c] = fmaf(J[c], wr, acc.s[c]);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        const float wj = w * J[c];
+#pragma unroll
+        for (int d = c; d < 6; ++d) acc.s[6 + tri(c, d)] = fmaf(wj, J[d], acc.s[6 + tri(c, d)]);
+    }
 }
 
 
@@ -228,6 +248,7 @@ struct LevelConst {
     const uint32_t* pts;        // the level's chunk-blocked candidates (deferred pass)
     Intrinsics k;
     double inv_fx, inv_fy, k01;  // 1/fx, 1/fy, -s/(fx fy): the f64 divisions of the per-pass serial part, done once per level
+    float huber_delta;
 };
 
 // Chooses Cu so that (bits(Cu) * rows + bits(Cv)) mod 2^32 plus any texel offset the level can produce (its image and the
@@ -271,8 +292,8 @@ constexpr int kNearWords = 32;  // flagged bitmap words a warp remembers per pas
 
 // One deferred candidate: the reference's own warp decides (lm_optimizer.rs:213-231); inside -> full evaluation into
 // `acc`, outside -> J J^T into h.
-template <bool kSkew>
-__device__ __forceinline__ void eval_deferred(int i, const LevelConst& lc, const Pose& model, Acc& acc, int& fixed, float (&h)[21]) {
+template <bool kSkew, bool kHuber>
+__device__ __forceinline__ void eval_deferred(int i, const LevelConst& lc, const Pose& model, Acc<kHuber>& acc, int& fixed, float (&h)[21]) {
     const uint32_t* __restrict__ pts = lc.pts;
     const Intrinsics k = lc.k;
     const int rows = int(lc.rows);
@@ -292,17 +313,23 @@ __device__ __forceinline__ void eval_deferred(int i, const LevelConst& lc, const
         const float top = fmaf(a, t01 - t00, t00), bot = fmaf(a, t11 - t10, t10);
         const float val = fmaf(b, bot - top, top);  // same lerp form as `back`
         const float r = val - float(rec_tmpl(pk));
-        acc.e = fmaf(r, r, acc.e);
         ++fixed;
-        if (kSkew) {
+        if constexpr (kHuber) {
             float J[6];
-            jacobian_centred<true>(gu, gv, ca, cb, rho, k, J);
-#pragma unroll
-            for (int q = 0; q < 6; ++q) acc.s[q] = fmaf(J[q], r, acc.s[q]);
+            jacobian_centred<kSkew>(gu, gv, ca, cb, rho, k, J);
+            accumulate_huber(acc, J, r, lc.huber_delta);
         } else {
-            accumulate_moments(acc, gu, gv, ca, cb, rho, r);
+            acc.e = fmaf(r, r, acc.e);
+            if constexpr (kSkew) {
+                float J[6];
+                jacobian_centred<true>(gu, gv, ca, cb, rho, k, J);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) acc.s[q] = fmaf(J[q], r, acc.s[q]);
+            } else {
+                accumulate_moments(acc, gu, gv, ca, cb, rho, r);
+            }
         }
-    } else {
+    } else if (!kHuber) {
         float J[6];
         jacobian_centred<kSkew>(gu, gv, ca, cb, rho, k, J);
 #pragma unroll
@@ -314,12 +341,12 @@ __device__ __forceinline__ void eval_deferred(int i, const LevelConst& lc, const
 
 // `wlist`: the (word, mask) pairs this warp flagged in the hot loop (n_words of them, only the first kNearWords stored);
 // `scratch`: this warp's ring memory (idle between passes), used as the compacted candidate list.
-template <bool kSkew>
+template <bool kSkew, bool kHuber>
 __device__ __noinline__ void deferred_pass(int warp, int lane, int first_stage, int stage_stride, int n_stages, uint32_t* __restrict__ bitmap,
-                                           const uint32_t* wlist, int n_words, uint32_t* scratch, Acc* acc_io, int* n_fix) {
+                                           const uint32_t* wlist, int n_words, uint32_t* scratch, Acc<kHuber>* acc_io, int* n_fix) {
     LmShared& S = lm_shared();
     const LevelConst& lc = s_lc;
-    Acc acc = *acc_io;
+    Acc<kHuber> acc = *acc_io;
     int fixed = 0;
     float h[21];
 #pragma unroll
@@ -348,7 +375,7 @@ __device__ __noinline__ void deferred_pass(int warp, int lane, int first_stage, 
             mask &= mask - 1u;
         }
         __syncwarp();
-        for (int e = lane; e < total; e += 32) eval_deferred<kSkew>(int(scratch[e]), lc, S.cand_model, acc, fixed, h);
+        for (int e = lane; e < total; e += 32) eval_deferred<kSkew, kHuber>(int(scratch[e]), lc, S.cand_model, acc, fixed, h);
     } else {
         // more flagged words than remembered: scan this warp's part of the bitmap, in groups of 128 slots (one uint4 of
         // bitmap words), one group per lane and round
@@ -369,18 +396,20 @@ __device__ __noinline__ void deferred_pass(int warp, int lane, int first_stage, 
                 while (bits) {
                     const int i = grp * 128 + 32 * j + __ffs(bits) - 1;
                     bits &= bits - 1u;
-                    if (i < lc.n) eval_deferred<kSkew>(i, lc, S.cand_model, acc, fixed, h);  // else: padding
+                    if (i < lc.n) eval_deferred<kSkew, kHuber>(i, lc, S.cand_model, acc, fixed, h);  // else: padding
                 }
             }
         }
     }
     __syncwarp();
+    if (!kHuber) {
 #pragma unroll
-    for (int c = 0; c < 21; ++c) {
-        float v = h[c];
+        for (int c = 0; c < 21; ++c) {
+            float v = h[c];
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        if (lane == 0) S.hout_pass[warp][c] += double(v);
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            if (lane == 0) S.hout_pass[warp][c] += double(v);
+        }
     }
     *acc_io = acc;
     *n_fix = fixed;
@@ -463,10 +492,10 @@ __device__ __forceinline__ FrontA front_a(uint32_t pk, float rho, uint32_t gr, c
 // `word` is the bitmap word of this call's 32 slots.
 // `old_words`: lane j holds the far-bitmap word of the stage's word j from the previous pass of the level; bit j of
 // `old_nz` says whether it is non-zero.  `j` = this call's word within the stage.
-template <bool kSkew>
+template <bool kSkew, bool kHuber>
 __device__ __forceinline__ void front_b(const FrontA& x, int word, int j, unsigned old_words, unsigned old_nz, const PassConst& lc,
                                         const Intrinsics& k, Defer& df, float* hs, int lane, Front& f) {
-    uint32_t pk = x.pk;
+    uint32_t pk = x.pk, gr = x.gr;
     float rho = x.rho, u = x.u, v = x.v;
     const bool ok = x.m < lc.lim_lo;  // false for NaN
     const unsigned not_ok = __ballot_sync(0xffffffffu, !ok);
@@ -480,7 +509,7 @@ __device__ __forceinline__ void front_b(const FrontA& x, int word, int j, unsign
         const int n_live = s_lc.n - 32 * word;
         const unsigned live_mask = n_live >= 32 ? 0xffffffffu : n_live <= 0 ? 0u : (1u << n_live) - 1u;
         const unsigned far_mask = __ballot_sync(0xffffffffu, far), near_mask = not_ok & ~far_mask & live_mask;
-        const unsigned flips = far_mask ^ old_far;
+        const unsigned flips = kHuber ? 0u : far_mask ^ old_far;  // (Huber weights: H is summed directly, nothing to maintain)
         if (flips) {
             const float sign = ((flips >> lane) & 1u) ? (far ? 1.0f : -1.0f) : 0.0f;
             add_outside<kSkew>(sign, x.gr, x.a, x.b, rho, k, hs);
@@ -504,6 +533,7 @@ __device__ __forceinline__ void front_b(const FrontA& x, int word, int j, unsign
             v = lc.zero_v;
             pk = 0u;   // template 0: r = 0 - 0
             rho = 0.0f;
+            gr = 0u;   // zero gradient: J = 0 (only the Huber path forms J on the common path)
         }
     }
     // floor and fraction without F2I / I2F (see kMagicBits)
@@ -516,15 +546,15 @@ __device__ __forceinline__ void front_b(const FrontA& x, int word, int j, unsign
     f.t01 = __ldg(p + lc.rows);
     f.t11 = __ldg(p + lc.rows + 1);
     f.pk = pk;
-    f.gr = x.gr;
+    f.gr = gr;
     f.a = x.a;
     f.b = x.b;
     f.rho = rho;
 }
 
 // back: bilinear sample, residual, accumulate.
-template <bool kSkew>
-__device__ __forceinline__ void back(const Front& f, const Intrinsics& k, Acc& acc) {
+template <bool kSkew, bool kHuber>
+__device__ __forceinline__ void back(const Front& f, const Intrinsics& k, float huber_delta, Acc<kHuber>& acc) {
     const float gu = rec_gx(f.gr), gv = rec_gy(f.gr);
     const float a = f.fa, b = f.fb;
     // bilinear sample in lerp form: the same interpolant as lm_optimizer.rs:241-246 (a along x, b along y) with 6 instead of
@@ -534,14 +564,20 @@ __device__ __forceinline__ void back(const Front& f, const Intrinsics& k, Acc& a
     const float top = fmaf(a, u2f(f.t01) - t00, t00), bot = fmaf(a, u2f(f.t11) - t10, t10);
     const float val = fmaf(b, bot - top, top);
     const float r = val - u2f(f.pk >> 24);
-    acc.e = fmaf(r, r, acc.e);
-    if (kSkew) {
+    if constexpr (kHuber) {
         float J[6];
-        jacobian_centred<true>(gu, gv, f.a, f.b, f.rho, k, J);
-#pragma unroll
-        for (int c = 0; c < 6; ++c) acc.s[c] = fmaf(J[c], r, acc.s[c]);
+        jacobian_centred<kSkew>(gu, gv, f.a, f.b, f.rho, k, J);
+        accumulate_huber(acc, J, r, huber_delta);
     } else {
-        accumulate_moments(acc, gu, gv, f.a, f.b, f.rho, r);
+        acc.e = fmaf(r, r, acc.e);
+        if constexpr (kSkew) {
+            float J[6];
+            jacobian_centred<true>(gu, gv, f.a, f.b, f.rho, k, J);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) acc.s[c] = fmaf(J[c], r, acc.s[c]);
+        } else {
+            accumulate_moments(acc, gu, gv, f.a, f.b, f.rho, r);
+        }
     }
 }
 
@@ -620,8 +656,9 @@ __device__ __noinline__ void lm_decide(LmShared& S, const AlignParams& P, const 
 }
 
 // Entry t of the finished pass (sum r^2, n_inside, g[6], H[21]) from the raw totals, f64; one lane of warp 0 per entry.
-template <bool kSkew>
+template <bool kSkew, bool kHuber>
 __device__ __forceinline__ double finish_entry(int t, const double* raw, const LevelConst& lc, const double* h_total) {
+    if (kHuber) return raw[t];  // sum rho, n_inside, g[6], H[21] were summed directly
     if (t < 2) return raw[t];
     if (t >= 8) {
         // H over the inside set = H_total (all candidates, per keyframe level) - H_outside; an empty inside set must give an
@@ -668,7 +705,7 @@ __device__ __forceinline__ float warp_matrix_entry(int e, const Pose& m, const L
     return float(r == 0 ? fx * a0 + s * a1 : r == 1 ? fy * a1 : a2);
 }
 
-template <bool kSkew>
+template <bool kSkew, bool kHuber>
 #ifdef VORS_MAXREG
 __global__ void __maxnreg__(VORS_MAXREG) k_align(const AlignParams P) {
 #else
@@ -741,6 +778,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                 c.inv_fx = 1.0 / double(k.fx);
                 c.inv_fy = 1.0 / double(k.fy);
                 c.k01 = -double(k.s) / (double(k.fx) * double(k.fy));
+                c.huber_delta = P.huber_delta;
                 s_lc = c;
                 S.cand_model = S.out_model;
                 S.init_phase = 1;  // also: the level's far bitmap and H_outside start empty
@@ -765,10 +803,12 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                     lc.magic_u = s_lc.magic_u; lc.magic_v = s_lc.magic_v; lc.rows = s_lc.rows; lc.img_biased = s_lc.img_biased;
                     lc.zero_u = s_lc.zero_u; lc.zero_v = s_lc.zero_v;
                     const Intrinsics k = s_lc.k;
-                    Acc acc;
+                    constexpr int kNumS = kHuber ? 27 : 11;  // per-thread sums besides the energy
+                    const float huber_delta = s_lc.huber_delta;
+                    Acc<kHuber> acc;
                     acc.e = 0.0f;
 #pragma unroll
-                    for (int c = 0; c < 11; ++c) acc.s[c] = 0.0f;
+                    for (int c = 0; c < kNumS; ++c) acc.s[c] = 0.0f;
                     Defer df;
                     df.near = lj.defer;
                     df.far = lj.defer_far;
@@ -803,8 +843,8 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                                 old = __ldcg(df.far + wi);
                             }
                             const FrontA xa = front_a(pk, rho, gr, M, lc);
-                            front_b<kSkew>(xa, wi, 0, old, old != 0u ? 1u : 0u, lc, k, df, hs, lane, fa);
-                            back<kSkew>(fa, k, acc);
+                            front_b<kSkew, kHuber>(xa, wi, 0, old, old != 0u ? 1u : 0u, lc, k, df, hs, lane, fa);
+                            back<kSkew, kHuber>(fa, k, huber_delta, acc);
                             n_slots += 32;
                         }
                     } else {
@@ -846,8 +886,8 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
     {                                                                                                 \
         const float* q = sp + (CH) * 3 * kChunk + (HALF) * 32;                                        \
         const FrontA xa = front_a(__float_as_uint(q[0]), q[kChunk], __float_as_uint(q[2 * kChunk]), M, lc); \
-        front_b<kSkew>(xa, kStageWordsBm * c + 2 * (CH) + (HALF), 2 * (CH) + (HALF), old_words, old_nz, lc, k, df, hs, lane, FNEW); \
-        back<kSkew>(FOLD, k, acc);                                                                    \
+        front_b<kSkew, kHuber>(xa, kStageWordsBm * c + 2 * (CH) + (HALF), 2 * (CH) + (HALF), old_words, old_nz, lc, k, df, hs, lane, FNEW); \
+        back<kSkew, kHuber>(FOLD, k, huber_delta, acc);                                               \
     }
 #pragma unroll(kChunkUnroll)
                             for (int ch = 0; ch < kStageChunks; ++ch) {
@@ -861,7 +901,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                             n_slots += kStageCand;
                         }
                     }
-                    back<kSkew>(fb, k, acc);
+                    back<kSkew, kHuber>(fb, k, huber_delta, acc);
 #if VORS_TIMING
                     const long long t_hot = clock64();
 #endif
@@ -878,8 +918,8 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                     }
                     if (df.n_near > 0) {  // warp-uniform
                         int n_fix = 0;
-                        Acc tmp = acc;  // only this copy has its address taken: `acc` itself stays in registers in the hot loop
-                        deferred_pass<kSkew>(warp, lane, gw, TW, n_stages, lj.defer, df.wlist, df.n_words,
+                        Acc<kHuber> tmp = acc;  // only this copy has its address taken: `acc` itself stays in registers in the hot loop
+                        deferred_pass<kSkew, kHuber>(warp, lane, gw, TW, n_stages, lj.defer, df.wlist, df.n_words,
                                              reinterpret_cast<uint32_t*>(&S.ring[warp][0]), &tmp, &n_fix);
                         acc = tmp;
 #pragma unroll
@@ -896,13 +936,13 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                     }
 #endif
                     // ---- reduce: warp shuffle, then per-CTA f64 sums in fixed order
-                    float vals[13];
+                    float vals[2 + kNumS];
                     vals[0] = acc.e;
                     vals[1] = lane == 0 ? float(n_slots - n_bad) : 0.0f;
 #pragma unroll
-                    for (int c = 0; c < 11; ++c) vals[2 + c] = acc.s[c];
+                    for (int c = 0; c < kNumS; ++c) vals[2 + c] = acc.s[c];
 #pragma unroll
-                    for (int c = 0; c < 13; ++c) {
+                    for (int c = 0; c < 2 + kNumS; ++c) {
                         float v = vals[c];
 #pragma unroll
                         for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
@@ -910,7 +950,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                     }
                     if (lane == 0) {
 #pragma unroll
-                        for (int c = 0; c < 13; ++c) S.warp_part[warp][c] = vals[c];
+                        for (int c = 0; c < 2 + kNumS; ++c) S.warp_part[warp][c] = vals[c];
                     }
                 }
 #if VORS_TIMING
@@ -929,7 +969,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
 #endif
                     for (int v = lane; v < kNumRaw; v += 32) {
                         double s = 0.0;
-                        if (v < 13) {
+                        if (v < (kHuber ? 29 : 13)) {
 #pragma unroll
                             for (int w = 0; w < kWarps; ++w) s += double(S.warp_part[w][v]);
                         } else {
@@ -965,7 +1005,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
 #if VORS_TIMING
                     const long long ts1 = clock64();
 #endif
-                    if (lane < kNumAcc) S.tot[lane] = finish_entry<kSkew>(lane, S.raw, s_lc, S.h_total);
+                    if (lane < kNumAcc) S.tot[lane] = finish_entry<kSkew, kHuber>(lane, S.raw, s_lc, S.h_total);
                     __syncwarp();
 #if VORS_TIMING
                     const long long ts2 = clock64();
@@ -1081,23 +1121,35 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
 
 }  // namespace
 
-static cudaError_t align_prepare() {
-    cudaError_t e = cudaFuncSetAttribute(k_align<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(LmShared)));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_align<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(LmShared)));
+template <typename F>
+static cudaError_t for_each_align_kernel(F f) {
+    cudaError_t e = f((const void*)k_align<false, false>);
+    if (e == cudaSuccess) e = f((const void*)k_align<true, false>);
+    if (e == cudaSuccess) e = f((const void*)k_align<false, true>);
+    if (e == cudaSuccess) e = f((const void*)k_align<true, true>);
     return e;
+}
+
+static cudaError_t align_prepare() {
+    return for_each_align_kernel(
+        [](const void* fn) { return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(LmShared))); });
 }
 
 cudaError_t align_query(AlignLaunchInfo* info) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    int sms = 0, per_sm = 0;
+    int sms = 0, per_sm = 1 << 30;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
     e = align_prepare();
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align<true>, kBlock, sizeof(LmShared));
+    e = for_each_align_kernel([&per_sm](const void* fn) {  // co-residency bound that holds for every variant
+        int n = 0;
+        const cudaError_t r = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, kBlock, sizeof(LmShared));
+        per_sm = n < per_sm ? n : per_sm;
+        return r;
+    });
     if (e != cudaSuccess) return e;
     info->block = kBlock;
     info->sm_count = sms;
@@ -1110,17 +1162,13 @@ cudaError_t launch_align(Launcher& L, const AlignParams& p, int n_teams) {
     ++L.launches;
     cudaError_t e = align_prepare();
     if (e != cudaSuccess) return e;
-    const void* fn = p.has_skew ? (const void*)k_align<true> : (const void*)k_align<false>;
-    if (p.team > 1) {
-        // co-residency of a team's CTAs is required by the counter barrier: cooperative launch checks it
-        void* args[] = {(void*)&p};
+    const bool huber = p.huber_delta > 0.0f;
+    const void* fn = huber ? (p.has_skew ? (const void*)k_align<true, true> : (const void*)k_align<false, true>)
+                           : (p.has_skew ? (const void*)k_align<true, false> : (const void*)k_align<false, false>);
+    void* args[] = {(void*)&p};
+    if (p.team > 1)  // co-residency of a team's CTAs is required by the counter barrier: cooperative launch checks it
         return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kBlock), args, sizeof(LmShared), L.stream);
-    }
-    if (p.has_skew)
-        k_align<true><<<grid, kBlock, sizeof(LmShared), L.stream>>>(p);
-    else
-        k_align<false><<<grid, kBlock, sizeof(LmShared), L.stream>>>(p);
-    return cudaGetLastError();
+    return cudaLaunchKernel(fn, dim3(grid), dim3(kBlock), args, sizeof(LmShared), L.stream);
 }
 
 }  // namespace vors

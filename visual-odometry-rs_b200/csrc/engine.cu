@@ -459,6 +459,7 @@ class Engine {
         p.max_iters = int(cfg.max_iters);
         p.fixed_iters = int(cfg.fixed_iters);
         p.has_skew = cfg.skew != 0.0f ? 1 : 0;
+        p.huber_delta = cfg.huber_delta > 0.0f ? cfg.huber_delta : 0.0f;
         return p;
     }
 

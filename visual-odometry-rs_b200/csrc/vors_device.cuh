@@ -120,6 +120,7 @@ struct AlignParams {
     float lm_coef_init, lm_coef_reject_mult, lm_coef_accept_mult, energy_delta_stop;
     int max_iters, fixed_iters;
     int has_skew;  // 0 selects the zero-skew Jacobian specialisation
+    float huber_delta;  // > 0 selects the Huber-weighted kernel variant (extension)
 };
 
 // Row J: warp_jacobian_at (inverse_compositional.rs:313-341), used by the align kernel (J is recomputed

@@ -51,7 +51,8 @@ class ConfigStruct(C.Structure):
         ("team_size", C.c_uint32),
         ("dso_nb_target", C.c_uint32),
         ("idepth_fusion", C.c_uint32),
-        ("reserved", C.c_uint32 * 2),
+        ("huber_delta", C.c_float),
+        ("reserved", C.c_uint32 * 1),
     ]
 
 
