@@ -54,6 +54,9 @@ extern "C" {
 /* inverse_depth.rs:81-98 `strategy_dso_mean` (Tracker default) / :105-152 `strategy_statistically_similar` (values whose
  * squared distance to the fused inverse depth reaches the fused variance discard the bloc; a discarded bloc is not a candidate) */
 enum { VORS_FUSION_DSO_MEAN = 0, VORS_FUSION_STATISTICALLY_SIMILAR = 1 };
+/* Scharr: gx = (3 (I[r-1,c+1] - I[r-1,c-1]) + 10 (I[r,c+1] - I[r,c-1]) + 3 (I[r+1,c+1] - I[r+1,c-1])) / 32, gy likewise along rows,
+ * i16 division truncating toward zero, 1-px border 0: the same scale as the centred difference it replaces. */
+enum { VORS_GRADIENT_REFERENCE = 0, VORS_GRADIENT_SCHARR = 1 };
 
 typedef struct vors_config {
     uint32_t nb_levels;                 /* Config::nb_levels */
@@ -79,7 +82,9 @@ typedef struct vors_config {
                                       lm_optimizer.rs:94-100): energy = mean rho_delta(r), g = sum w J r, H = sum w J J^T with
                                       w = min(1, delta / |r|) (grey levels).  0 = the reference's plain L2.  Excluded from parity
                                       with the reference; checked against the oracle's same option. */
-    uint32_t reserved[1];
+    uint32_t gradient_operator;    /* VORS_GRADIENT_*: 0 = the Tracker's recipe (centred differences at level 0, 2x2-bloc differences of
+                                      the finer image above, inverse_compositional.rs:112-117); 1 = 3x3 Scharr on every level's own
+                                      image (the north_star's other extra; not in the reference, excluded from parity with it) */
 } vors_config;
 
 /* Replaces `Iso3 = Isometry3<f32>` (src/misc/type_aliases.rs:30); printed by the reference as

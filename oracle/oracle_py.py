@@ -38,7 +38,7 @@ class Config(C.Structure):
         ("dso_nb_target", C.c_uint32),
         ("idepth_fusion", C.c_uint32),
         ("huber_delta", C.c_float),
-        ("reserved", C.c_uint32 * 1),
+        ("gradient_operator", C.c_uint32),
     ]
 
 
@@ -102,6 +102,7 @@ def _load(name: str) -> C.CDLL:
         "ref_pyramid_shapes": (C.c_int, [C.c_int, C.c_int, C.c_int, _i32p, _i32p]),
         "ref_mean_pyramid": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, _u8p]),
         "ref_gradient_centered": (None, [_u8p, C.c_int, C.c_int, _i16p, _i16p]),
+        "ref_gradient_scharr": (None, [_u8p, C.c_int, C.c_int, _i16p, _i16p]),
         "ref_gradients_tracker": (None, [_u8p, C.c_int, C.c_int, C.c_int, _i16p, _i16p, _u16p]),
         "ref_squared_norm_direct": (None, [_u8p, C.c_int, C.c_int, _u16p]),
         "ref_gradients_squared_norm_example": (None, [_u8p, C.c_int, C.c_int, C.c_int, _u16p]),
@@ -207,6 +208,14 @@ def mean_pyramid(img: np.ndarray, max_levels: int, fast: bool = False):
     n = lib(fast).ref_mean_pyramid(_cm(img), rows, cols, max_levels, out)
     assert n == len(shapes)
     return split_concat(out, shapes)
+
+
+def gradient_scharr(img):
+    rows, cols = img.shape
+    gx = np.zeros(rows * cols, np.int16)
+    gy = np.zeros(rows * cols, np.int16)
+    lib().ref_gradient_scharr(_cm(img), rows, cols, gx, gy)
+    return _from_cm(gx, rows, cols), _from_cm(gy, rows, cols)
 
 
 def gradients_tracker(pyr):

@@ -143,15 +143,34 @@ Mat<uint16_t> squared_norm_direct(const Mat<uint8_t>& im) {
 
 // multires.rs:112-126 `gradients_xy` + inverse_compositional.rs:112-117: G[0]=centered(I[0]),
 // G[l]=halve(I[l-1], bloc_x / bloc_y) for l>=1, g2[l]=squared_norm(G[l]).
+// Extension (not in the reference; the north_star's "Scharr"): 3x3 Scharr operator on a level's own image, normalised by 32 so
+// that it has the scale of the centred difference, i16 division truncating toward zero, 1-px border 0.
+void gradient_scharr(const Mat<uint8_t>& im, Mat<int16_t>& gx, Mat<int16_t>& gy) {
+    gx = Mat<int16_t>(im.rows, im.cols);
+    gy = Mat<int16_t>(im.rows, im.cols);
+    for (int c = 1; c + 1 < im.cols; ++c)
+        for (int r = 1; r + 1 < im.rows; ++r) {
+            auto I = [&](int dr, int dc) { return int(im(r + dr, c + dc)); };
+            const int sx = 3 * (I(-1, 1) - I(-1, -1)) + 10 * (I(0, 1) - I(0, -1)) + 3 * (I(1, 1) - I(1, -1));
+            const int sy = 3 * (I(1, -1) - I(-1, -1)) + 10 * (I(1, 0) - I(-1, 0)) + 3 * (I(1, 1) - I(-1, 1));
+            gx(r, c) = int16_t(sx / 32);
+            gy(r, c) = int16_t(sy / 32);
+        }
+}
+
 void gradients_tracker(const std::vector<Mat<uint8_t>>& pyr, std::vector<Mat<int16_t>>& gxs,
-                       std::vector<Mat<int16_t>>& gys, std::vector<Mat<uint16_t>>& g2s) {
+                       std::vector<Mat<int16_t>>& gys, std::vector<Mat<uint16_t>>& g2s, bool scharr = false) {
     const size_t L = pyr.size();
     gxs.assign(L, {});
     gys.assign(L, {});
-    gradient_centered(pyr[0], gxs[0], gys[0]);
-    for (size_t l = 1; l < L; ++l) {
-        halve<uint8_t, int16_t>(pyr[l - 1], bloc_x, gxs[l]);
-        halve<uint8_t, int16_t>(pyr[l - 1], bloc_y, gys[l]);
+    if (scharr) {
+        for (size_t l = 0; l < L; ++l) gradient_scharr(pyr[l], gxs[l], gys[l]);
+    } else {
+        gradient_centered(pyr[0], gxs[0], gys[0]);
+        for (size_t l = 1; l < L; ++l) {
+            halve<uint8_t, int16_t>(pyr[l - 1], bloc_x, gxs[l]);
+            halve<uint8_t, int16_t>(pyr[l - 1], bloc_y, gys[l]);
+        }
     }
     g2s.clear();
     for (size_t l = 0; l < L; ++l) g2s.push_back(squared_norm(gxs[l], gys[l]));
@@ -622,7 +641,7 @@ std::unique_ptr<Keyframe> precompute_multires_data(const ref_config& cfg, const 
     kf->huber_delta = cfg.huber_delta;
     std::vector<Mat<int16_t>> gxs, gys;
     std::vector<Mat<uint16_t>> g2s;
-    gradients_tracker(img_multires, gxs, gys, g2s);
+    gradients_tracker(img_multires, gxs, gys, g2s, cfg.gradient_operator == 1);
 
     // :120-125 candidates::select(...).pop()  (extensions: dense = all pixels; dso at level 0)
     Mat<uint8_t> mask0;
@@ -1080,6 +1099,13 @@ int ref_mean_pyramid(const uint8_t* img, int rows, int cols, int max_levels, uin
 void ref_gradient_centered(const uint8_t* img, int rows, int cols, int16_t* gx, int16_t* gy) {
     Mat<int16_t> x, y;
     gradient_centered(mat_from(img, rows, cols), x, y);
+    std::memcpy(gx, x.d.data(), x.size() * 2);
+    std::memcpy(gy, y.d.data(), y.size() * 2);
+}
+
+void ref_gradient_scharr(const uint8_t* img, int rows, int cols, int16_t* gx, int16_t* gy) {
+    Mat<int16_t> x, y;
+    gradient_scharr(mat_from(img, rows, cols), x, y);
     std::memcpy(gx, x.d.data(), x.size() * 2);
     std::memcpy(gy, y.d.data(), y.size() * 2);
 }

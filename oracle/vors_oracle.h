@@ -58,7 +58,7 @@ typedef struct ref_config {
     uint32_t dso_nb_target;
     uint32_t idepth_fusion; /* 0 strategy_dso_mean (Tracker), 1 strategy_statistically_similar (inverse_depth.rs:105-152) */
     float huber_delta;      /* > 0: Huber weights (extension, not in the reference); 0 = plain L2 like the reference */
-    uint32_t reserved[1];
+    uint32_t gradient_operator; /* 0 the Tracker's recipe; 1 Scharr 3x3 on every level (extension, not in the reference) */
 } ref_config;
 
 typedef struct ref_pose {
@@ -93,6 +93,8 @@ void ref_set_accum_f64(int on);
 int ref_pyramid_shapes(int rows, int cols, int max_levels, int* out_rows, int* out_cols);
 int ref_mean_pyramid(const uint8_t* img, int rows, int cols, int max_levels, uint8_t* out_concat);
 void ref_gradient_centered(const uint8_t* img, int rows, int cols, int16_t* gx, int16_t* gy);
+/* Extension (gradient_operator = 1, not in the reference): 3x3 Scharr / 32, truncating, 1-px border 0. */
+void ref_gradient_scharr(const uint8_t* img, int rows, int cols, int16_t* gx, int16_t* gy);
 /* Tracker recipe: level 0 centered, level l>=1 2x2-block gradients of level l-1. */
 void ref_gradients_tracker(const uint8_t* pyr_concat, int rows, int cols, int n_levels,
                            int16_t* gx_concat, int16_t* gy_concat, uint16_t* g2_concat);

@@ -591,6 +591,35 @@ def test_statistically_similar_fusion_option(vb, oracle, mode):
     _pose_close(t.current_frame()[1].as_array(), ot.current_frame()[1].as_array(), oracle)
 
 
+@pytest.mark.parametrize("shape", [(120, 160), (75, 101)])
+def test_scharr_gradient_option(vb, oracle, shape):
+    """gradient_operator = 1 (3x3 Scharr on every level; an extension, the reference has none): candidate mask, candidate lists
+    and gathered gradients bit-identical to the oracle's same option, Jacobians and tracked pose within tolerance."""
+    rows, cols = shape
+    scene, frames, _ = synth.make_sequence(seed=77, n_frames=3, rows=rows, cols=cols, step_v=0.01, step_w=0.006)
+    cfg, ocfg = _cfgs(vb, oracle, scene, nb_levels=3, gradient_operator=1)
+    kf, okf = vb.Keyframe(cfg, frames[0][1], frames[0][0]), oracle.Keyframe(ocfg, frames[0][1], frames[0][0])
+    assert np.array_equal(kf.mask0(), okf.mask0())
+    ref_mask = oracle.Keyframe(_cfgs(vb, oracle, scene, nb_levels=3)[1], frames[0][1], frames[0][0]).mask0()
+    assert not np.array_equal(okf.mask0(), ref_mask)  # a different operator selects different candidates
+    pyr = oracle.mean_pyramid(frames[0][0], 3)
+    for l in range(3):
+        xy, idepth, grad, tmpl = kf.points(l)
+        oxy, oid, ojac = okf.points(l)
+        assert np.array_equal(xy, oxy) and np.array_equal(idepth, oid)
+        sx, sy = oracle.gradient_scharr(pyr[l])
+        assert np.array_equal(grad[:, 0], sx[oxy[:, 1], oxy[:, 0]]) and np.array_equal(grad[:, 1], sy[oxy[:, 1], oxy[:, 0]])
+        jac = kf.jacobians(l)
+        assert np.all(np.abs(jac - ojac) <= 2e-6 * (np.abs(ojac).max(0) + 1e-30) + 1e-6 * np.abs(ojac))
+    t = cfg.init(0.0, frames[0][1], 0.0, frames[0][0])
+    ot = oracle.Tracker(ocfg, 0.0, frames[0][1], 0.0, frames[0][0])
+    for k in (1, 2):
+        st = t.track(float(k), frames[k][1], float(k), frames[k][0])
+        ost = ot.track(float(k), frames[k][1], float(k), frames[k][0])
+        assert st.status == ost[1].status == 0
+    _pose_close(t.current_frame()[1].as_array(), ot.current_frame()[1].as_array(), oracle)
+
+
 @pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("skew", [0.0, 0.4])
 def test_huber_option_matches_oracle(vb, oracle, mode, skew):

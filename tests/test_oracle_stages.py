@@ -189,6 +189,25 @@ def test_statistically_similar_fusion_matches_independent_restatement(oracle, sm
     assert kf.n_points(1) < kf0.n_points(1)
 
 
+def test_scharr_option_of_the_oracle(oracle):
+    """gradient_operator = 1 (an extension; the reference has no Scharr): the oracle's operator against a numpy restatement,
+    including the truncating division and the zero border, on noise and on a ramp (where Scharr equals the centred difference)."""
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (37, 53), dtype=np.uint8)
+    gx, gy = oracle.gradient_scharr(img)
+    I = img.astype(np.int32)
+    sx = 3 * (I[:-2, 2:] - I[:-2, :-2]) + 10 * (I[1:-1, 2:] - I[1:-1, :-2]) + 3 * (I[2:, 2:] - I[2:, :-2])
+    sy = 3 * (I[2:, :-2] - I[:-2, :-2]) + 10 * (I[2:, 1:-1] - I[:-2, 1:-1]) + 3 * (I[2:, 2:] - I[:-2, 2:])
+    trunc = lambda v: (np.sign(v) * (np.abs(v) // 32)).astype(np.int16)
+    wx = np.zeros_like(gx); wy = np.zeros_like(gy)
+    wx[1:-1, 1:-1] = trunc(sx); wy[1:-1, 1:-1] = trunc(sy)
+    assert np.array_equal(gx, wx) and np.array_equal(gy, wy)
+    ramp = (np.arange(53, dtype=np.int32)[None, :] * 2 + np.arange(37, dtype=np.int32)[:, None]).astype(np.uint8)
+    rx, ry = oracle.gradient_scharr(ramp)
+    assert np.all(rx[1:-1, 1:-1] == 2) and np.all(ry[1:-1, 1:-1] == 1)
+    assert not rx[0].any() and not rx[:, 0].any() and not ry[-1].any() and not ry[:, -1].any()
+
+
 def test_huber_option_of_the_oracle(oracle, small_pair):
     """huber_delta (an extension; the reference is plain L2): a huge delta reproduces the L2 evaluation exactly, a small
     one lowers the energy and shrinks g and H (weights <= 1), and H stays symmetric; the default is L2."""

@@ -197,6 +197,7 @@ class Engine {
             return fail(VORS_E_CUDA, "no CUDA device available (libvors_b200 has no CPU fallback)");
         }
         if (cfg.idepth_fusion > VORS_FUSION_STATISTICALLY_SIMILAR) return fail(VORS_E_INVALID, "unknown idepth_fusion");
+        if (cfg.gradient_operator > VORS_GRADIENT_SCHARR) return fail(VORS_E_INVALID, "unknown gradient_operator");
         if (cfg.device >= 0) {
             if (cfg.device >= count) return fail(VORS_E_INVALID, "device ordinal out of range");
             device = cfg.device;
@@ -374,7 +375,8 @@ class Engine {
     // ---- keyframe precompute (inverse_compositional.rs:105-161) for the m streams in d_items --------
     int precompute(const uint16_t* depth_slab, int m) {
         const int dense = cfg.candidate_mode == VORS_CANDIDATES_DENSE;
-        launch_gradients(L, g, d_pyr, d_grad, (dense || cfg.candidate_mode == VORS_CANDIDATES_DSO) ? nullptr : d_g2, d_items, m);
+        launch_gradients(L, g, cfg.gradient_operator == VORS_GRADIENT_SCHARR ? 1 : 0, d_pyr, d_grad,
+                         (dense || cfg.candidate_mode == VORS_CANDIDATES_DSO) ? nullptr : d_g2, d_items, m);
         const bool dso = cfg.candidate_mode == VORS_CANDIDATES_DSO;
         if (dso) {
             // BASELINE config 3: DSO selection on the level-0 gradient magnitude (examples/candidates_dso.rs:40-60:
@@ -924,7 +926,7 @@ int vors_gradients(const uint8_t* img, uint32_t rows, uint32_t cols, uint32_t ma
     const int levels = e->g.L;
     if (rc == VORS_OK) {
         launch_pyramid(e->L, e->g, e->d_pyr, nullptr, 1);
-        launch_gradients(e->L, e->g, e->d_pyr, e->d_grad, e->d_g2, nullptr, 1);
+        launch_gradients(e->L, e->g, 0, e->d_pyr, e->d_grad, e->d_g2, nullptr, 1);
         const size_t P = size_t(e->g.pix_total);
         std::vector<uint32_t> grad(P);
         cudaError_t ce = cudaMemcpyAsync(grad.data(), e->d_grad, P * 4, cudaMemcpyDeviceToHost, e->L.stream);

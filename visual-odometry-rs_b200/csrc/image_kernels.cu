@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(256) k_pyramid_fused(const Geom g, int l_first
 // one launch.  Level 0: gradient::centered (gradient.rs:15-33), i16 division truncating toward zero,
 // 1-px border 0.  Level l >= 1: bloc_x / bloc_y of the level l-1 image (gradient.rs:74-93).
 // g2 = (gx*gx + gy*gy) as u16 (gradient.rs:38-44).
-__global__ void k_gradients(const Geom g, const uint8_t* __restrict__ pyr_slab, uint32_t* __restrict__ grad_slab,
+// `scharr` (extension, vors_config.gradient_operator = 1): 3x3 Scharr / 32 on every level's own image instead.
+__global__ void k_gradients(const Geom g, int scharr, const uint8_t* __restrict__ pyr_slab, uint32_t* __restrict__ grad_slab,
                             uint16_t* __restrict__ g2_slab, const int* __restrict__ items) {
     const size_t base = size_t(item_of(items, blockIdx.y)) * g.pix_stride;
     const uint8_t* pyr = pyr_slab + base;
@@ -119,7 +120,14 @@ __global__ void k_gradients(const Geom g, const uint8_t* __restrict__ pyr_slab, 
         const int R = g.rows[l], C = g.cols[l];
         const int x = o / R, y = o - x * R;
         int gx = 0, gy = 0;
-        if (l == 0) {
+        if (scharr) {
+            if (x > 0 && x < C - 1 && y > 0 && y < R - 1) {
+                const uint8_t* p = pyr + g.off[l] + size_t(x) * R + y;  // p[dc * R + dr]
+                const int tl = p[-R - 1], ml = p[-R], bl = p[-R + 1], tc = p[-1], bc = p[1], tr = p[R - 1], mr = p[R], br = p[R + 1];
+                gx = (3 * (tr - tl) + 10 * (mr - ml) + 3 * (br - bl)) / 32;
+                gy = (3 * (bl - tl) + 10 * (bc - tc) + 3 * (br - tr)) / 32;
+            }
+        } else if (l == 0) {
             if (x > 0 && x < C - 1 && y > 0 && y < R - 1) {
                 const uint8_t* p = pyr + size_t(x) * R + y;
                 gx = (int(p[R]) - int(p[-R])) / 2;  // right - left, C++ `/` truncates like Rust
@@ -521,10 +529,10 @@ void launch_pyramid_levelwise(Launcher& L, const Geom& g, uint8_t* pyr_slab, con
         ++L.launches;
     }
 }
-void launch_gradients(Launcher& L, const Geom& g, const uint8_t* pyr_slab, uint32_t* grad_slab, uint16_t* g2_slab, const int* items,
+void launch_gradients(Launcher& L, const Geom& g, int scharr, const uint8_t* pyr_slab, uint32_t* grad_slab, uint16_t* g2_slab, const int* items,
                       int m) {
     dim3 grid(grid_for(g.pix_total, 256), m);
-    k_gradients<<<grid, 256, 0, L.stream>>>(g, pyr_slab, grad_slab, g2_slab, items);
+    k_gradients<<<grid, 256, 0, L.stream>>>(g, scharr, pyr_slab, grad_slab, g2_slab, items);
     ++L.launches;
 }
 void launch_c2f(Launcher& L, const Geom& g, uint16_t thresh, const uint16_t* g2_slab, uint8_t* mask_slab, const int* items, int m) {

@@ -173,7 +173,7 @@ void launch_transpose_u16(Launcher& L, const uint16_t* in_rowmajor, uint16_t* ou
 void launch_copy_items_u16(Launcher& L, const uint16_t* in, uint16_t* out_slab, size_t out_stride, const int* items, int m,
                            size_t count);
 void launch_pyramid(Launcher& L, const Geom& g, uint8_t* pyr_slab, const int* items, int m);
-void launch_gradients(Launcher& L, const Geom& g, const uint8_t* pyr_slab, uint32_t* grad_slab, uint16_t* g2_slab,
+void launch_gradients(Launcher& L, const Geom& g, int scharr, const uint8_t* pyr_slab, uint32_t* grad_slab, uint16_t* g2_slab,
                       const int* items, int m);
 void launch_c2f(Launcher& L, const Geom& g, uint16_t thresh, const uint16_t* g2_slab, uint8_t* mask_slab, const int* items,
                 int m);

@@ -52,7 +52,7 @@ class ConfigStruct(C.Structure):
         ("dso_nb_target", C.c_uint32),
         ("idepth_fusion", C.c_uint32),
         ("huber_delta", C.c_float),
-        ("reserved", C.c_uint32 * 1),
+        ("gradient_operator", C.c_uint32),
     ]
 
 
