@@ -351,16 +351,10 @@ __device__ __noinline__ void deferred_pass(int warp, int lane, int first_stage, 
     float h[21];
 #pragma unroll
     for (int c = 0; c < 21; ++c) h[c] = 0.0f;
-    if (n_words <= kNearWords) {
-        // common case: compact the flagged slots of the remembered words into a list, one candidate per lane and round
-        uint32_t word = 0u, mask = 0u;
-        if (lane < n_words) {
-            word = wlist[2 * lane];
-            mask = wlist[2 * lane + 1];
-            bitmap[word] = 0u;  // leave the bitmap all-zero for the next pass
-            const int base = int(word) * 32;
-            if (base + 32 > lc.n) mask = base >= lc.n ? 0u : (mask & ((1u << (lc.n - base)) - 1u));  // padding slots
-        }
+    // One round: every lane brings one flagged bitmap word (`mask` over the 32 slots starting at slot `base`); the set bits of
+    // the whole warp are compacted into `scratch` (at most 1024 entries) and evaluated one candidate per lane and step.
+    auto round = [&](uint32_t mask, int base) {
+        if (base + 32 > lc.n) mask = base >= lc.n ? 0u : (mask & ((1u << (lc.n - base)) - 1u));  // padding slots
         const int cnt = __popc(mask);
         int incl = cnt;
 #pragma unroll
@@ -371,34 +365,42 @@ __device__ __noinline__ void deferred_pass(int warp, int lane, int first_stage, 
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         int off = incl - cnt;
         while (mask) {
-            scratch[off++] = word * 32u + uint32_t(__ffs(mask) - 1);
+            scratch[off++] = uint32_t(base) + uint32_t(__ffs(mask) - 1);
             mask &= mask - 1u;
         }
         __syncwarp();
         for (int e = lane; e < total; e += 32) eval_deferred<kSkew, kHuber>(int(scratch[e]), lc, S.cand_model, acc, fixed, h);
+        __syncwarp();
+    };
+    if (n_words <= kNearWords) {
+        // common case: the flagged words were remembered
+        uint32_t word = 0u, mask = 0u;
+        if (lane < n_words) {
+            word = wlist[2 * lane];
+            mask = wlist[2 * lane + 1];
+            bitmap[word] = 0u;  // leave the bitmap all-zero for the next pass
+        }
+        round(mask, int(word) * 32);
     } else {
-        // more flagged words than remembered: scan this warp's part of the bitmap, in groups of 128 slots (one uint4 of
-        // bitmap words), one group per lane and round
+        // more flagged words than remembered (e.g. a static camera: the x = 0 column and the y = 0 row sit exactly on the
+        // inside-test boundary): scan this warp's part of the bitmap, one group of 128 slots (a uint4 of bitmap words) per lane
         constexpr int kGroups = kStageCand / 128;
         const int my_groups = first_stage < n_stages ? ((n_stages - first_stage + stage_stride - 1) / stage_stride) * kGroups : 0;
-        for (int g0 = 0; g0 < my_groups; g0 += 32) {
+        for (int g0 = 0; g0 < my_groups; g0 += 32) {  // warp-uniform trip count
             const int gi = g0 + lane;
-            if (gi >= my_groups) continue;
-            const int grp = (first_stage + (gi / kGroups) * stage_stride) * kGroups + gi % kGroups;  // 128-slot group index in the level
-            uint4* wp = reinterpret_cast<uint4*>(bitmap) + grp;
-            const uint4 w4 = *wp;
-            if ((w4.x | w4.y | w4.z | w4.w) == 0u) continue;
-            *wp = make_uint4(0u, 0u, 0u, 0u);
-            const uint32_t words[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll 1
-            for (int j = 0; j < 4; ++j) {
-                uint32_t bits = words[j];
-                while (bits) {
-                    const int i = grp * 128 + 32 * j + __ffs(bits) - 1;
-                    bits &= bits - 1u;
-                    if (i < lc.n) eval_deferred<kSkew, kHuber>(i, lc, S.cand_model, acc, fixed, h);  // else: padding
-                }
+            int grp = 0;
+            uint4 w4 = make_uint4(0u, 0u, 0u, 0u);
+            if (gi < my_groups) {
+                grp = (first_stage + (gi / kGroups) * stage_stride) * kGroups + gi % kGroups;  // 128-slot group index in the level
+                uint4* wp = reinterpret_cast<uint4*>(bitmap) + grp;
+                w4 = *wp;
+                if (w4.x | w4.y | w4.z | w4.w) *wp = make_uint4(0u, 0u, 0u, 0u);
             }
+            if (!__any_sync(0xffffffffu, (w4.x | w4.y | w4.z | w4.w) != 0u)) continue;
+            round(w4.x, grp * 128);
+            round(w4.y, grp * 128 + 32);
+            round(w4.z, grp * 128 + 64);
+            round(w4.w, grp * 128 + 96);
         }
     }
     __syncwarp();
