@@ -48,6 +48,9 @@ namespace {
 #ifndef VORS_MIN_CTAS
 #define VORS_MIN_CTAS 2
 #endif
+#ifndef VORS_X_MAGIC
+#define VORS_X_MAGIC 0  // 1: x through the 2^23 magic number (2 LOP3 + FADD) instead of LOP3 + I2FP
+#endif
 #ifndef VORS_STAGES
 #define VORS_STAGES 2
 #endif
@@ -84,7 +87,7 @@ struct LmShared {
     int n_passes;
     int trace_len;
     unsigned long long point_passes;
-    float warp_part[kWarps][32];   // per-warp sums of the pass accumulators (E, n, 11 moments / g[6] / Huber: g[6] and H[21])
+    float warp_part[kWarps][32];   // per-warp sums of the pass accumulators (E, n, 9 moments / g[6] / Huber: g[6] and H[21])
     double hout[kWarps][21];       // per-warp sum of J J^T over the candidates outside for sure, cumulative over a level's passes
     double hout_pass[kWarps][21];  // per-warp sum of J J^T over this pass's deferred candidates that turned out outside
     double h_total[21];            // the level's H_total (k_h_total), cached for the per-pass serial part
@@ -154,28 +157,30 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 __device__ __host__ constexpr int tri(int a, int b) { return a * 6 - a * (a - 1) / 2 + (b - a); }
 
 // Raw per-thread accumulators of one pass.  Zero skew (every intrinsics set the reference ships): instead of the
-// six Jacobian entries, eleven moments of (p, q) = (gu r, gv r) from which g = sum J r is assembled once per pass
-// in f64 (J is linear in (gu, gv) with coefficients polynomial in a = x - cu, b = y - cv and idepth,
-// inverse_compositional.rs:326-340) - 16 instead of 29 instructions per candidate.  With skew the plain g[6].
+// six Jacobian entries, nine moments of (p, q) = (gu r, gv r) and s = a p + b q from which g = sum J r is assembled once
+// per pass in f64 (J is linear in (gu, gv) with coefficients polynomial in a = x - cu, b = y - cv and idepth,
+// inverse_compositional.rs:326-340; a b p + b^2 q = b s and a^2 p + a b q = a s) - 13 instead of 29 instructions per
+// candidate.  With skew the plain g[6].
 // kHuber (extension, vors_config.huber_delta > 0): the weights depend on the residual, so neither the moments nor
 // H = H_total - H_outside apply; g[6] and the 21 entries of H are summed directly (s[0..5], s[6..26]).
 template <bool kHuber>
 struct Acc {
     float e;
-    float s[kHuber ? 27 : 11];
+    float s[kHuber ? 27 : 9];
 };
-enum { kSrp, kSrq, kSrt, kSabp, kSbbq, kSq, kSaap, kSp, kSabq, kSbp, kSaq };
+enum { kSrp, kSrq, kSrs, kSbs, kSas, kSq, kSp, kSbp, kSaq };
+constexpr int kNumMoments = 9;
+constexpr int kRawH = 2 + kNumMoments;  // raw[kRawH ..]: H_outside[21]
+static_assert(kRawH + 21 == kNumRaw, "raw totals: sum r^2, n_inside, moments, H_outside");
 
 __device__ __forceinline__ void accumulate_moments(Acc<false>& acc, float gu, float gv, float a, float b, float rho, float r) {
     const float p = gu * r, q = gv * r;
-    const float ap = a * p, bq = b * q;
+    const float s = fmaf(a, p, b * q);
     acc.s[kSrp] = fmaf(rho, p, acc.s[kSrp]);
     acc.s[kSrq] = fmaf(rho, q, acc.s[kSrq]);
-    acc.s[kSrt] = fmaf(rho, ap + bq, acc.s[kSrt]);
-    acc.s[kSaap] = fmaf(a, ap, acc.s[kSaap]);
-    acc.s[kSbbq] = fmaf(b, bq, acc.s[kSbbq]);
-    acc.s[kSabp] = fmaf(b, ap, acc.s[kSabp]);
-    acc.s[kSabq] = fmaf(a, bq, acc.s[kSabq]);
+    acc.s[kSrs] = fmaf(rho, s, acc.s[kSrs]);
+    acc.s[kSbs] = fmaf(b, s, acc.s[kSbs]);
+    acc.s[kSas] = fmaf(a, s, acc.s[kSas]);
     acc.s[kSp] += p;
     acc.s[kSq] += q;
     acc.s[kSbp] = fmaf(b, p, acc.s[kSbp]);
@@ -236,8 +241,9 @@ constexpr uint32_t kMagicBits = 0x4B000000u;  // 2^23
 // Per-level constants of the pass (warp-uniform).
 struct LevelConst {
     float cx, cy;
-    float su, sv;        // 2 / (W-2), 2 / (H-2): maps the inside range [0, W-2) x [0, H-2) to (-1, 1)^2
-    float lim_lo, lim_hi;  // 1 -+ band: inside for sure below lim_lo, outside for sure above lim_hi
+    float hu, hv;        // centre of the inside range [0, W-2) x [0, H-2): (W-2) / 2, (H-2) / 2
+    float lo_u, lo_v;    // |u - hu| < lo_u and |v - hv| < lo_v: inside for sure (half extent - band)
+    float hi_u, hi_v;    // |u - hu| > hi_u or  |v - hv| > hi_v: outside for sure (half extent + band)
     float wm2, hm2;
     float zero_u, zero_v;
     float magic_u, magic_v;     // floor constants Cu, Cv (see kMagicBits)
@@ -421,7 +427,7 @@ __device__ __noinline__ void deferred_pass(int warp, int lane, int first_stage, 
 
 // Per-level constants the common path keeps in registers.
 struct PassConst {
-    float cx, cy, su, sv, lim_lo, magic_u, magic_v, zero_u, zero_v;
+    float cx, cy, hu, hv, lo_u, lo_v, magic_u, magic_v, zero_u, zero_v;
     uint32_t rows;
     const uint8_t* img_biased;
 };
@@ -466,11 +472,16 @@ __device__ __forceinline__ void add_outside(float sign, uint32_t gr, float a, fl
 // `back` of the previous candidate (issued between the two halves).
 struct FrontA {
     uint32_t pk, gr;
-    float rho, a, b, u, v, m;
+    float rho, a, b, u, v;
+    bool ok;  // inside for sure (false for NaN)
 };
 __device__ __forceinline__ FrontA front_a(uint32_t pk, float rho, uint32_t gr, const float (&M)[12], const PassConst& lc) {
     // int -> float through the 2^23 magic number: one LOP3 (ALU pipe) + one FADD (FMA pipe) instead of mask + I2F
+#if VORS_X_MAGIC
     const float x = __uint_as_float((pk & 0xFFFu) | 0x4B000000u) - 8388608.0f;
+#else
+    const float x = float(pk & 0xFFFu);
+#endif
     const float y = float((pk >> 12) & 0xFFFu);
     const float a = x - lc.cx, b = y - lc.cy;  // camera.rs:135-140 starts from these rounded differences too
     const float U = fmaf(M[0], a, fmaf(M[1], b, fmaf(M[3], rho, M[2])));
@@ -480,8 +491,8 @@ __device__ __forceinline__ FrontA front_a(uint32_t pk, float rho, uint32_t gr, c
     FrontA o;
     o.u = fmaf(U, iw, lc.cx);
     o.v = fmaf(V, iw, lc.cy);
-    // lm_optimizer.rs:231: inside iff 0 <= floor(u) < W-2 and 0 <= floor(v) < H-2; here: inside with a margin
-    o.m = fmaxf(fabsf(fmaf(o.u, lc.su, -1.0f)), fabsf(fmaf(o.v, lc.sv, -1.0f)));
+    // lm_optimizer.rs:231: inside iff 0 <= floor(u) < W-2 and 0 <= floor(v) < H-2; here: inside with a margin of kBandPx
+    o.ok = (fabsf(o.u - lc.hu) < lc.lo_u) & (fabsf(o.v - lc.hv) < lc.lo_v);
     o.pk = pk;
     o.gr = gr;
     o.rho = rho;
@@ -499,14 +510,14 @@ __device__ __forceinline__ void front_b(const FrontA& x, int word, int j, unsign
                                         const Intrinsics& k, Defer& df, float* hs, int lane, Front& f) {
     uint32_t pk = x.pk, gr = x.gr;
     float rho = x.rho, u = x.u, v = x.v;
-    const bool ok = x.m < lc.lim_lo;  // false for NaN
+    const bool ok = x.ok;
     const unsigned not_ok = __ballot_sync(0xffffffffu, !ok);
-    if (not_ok | ((old_nz >> j) & 1u)) {  // warp-uniform, rare
+    if (not_ok | (old_nz & (1u << j))) {  // warp-uniform, rare
         const unsigned old_far = __shfl_sync(0xffffffffu, old_words, j);
         // H over the inside set = H_total - H_outside (lm_optimizer.rs:100 sums J J^T over the inside set).  H_outside is
         // maintained incrementally across the passes of a level: only candidates that were outside for sure in the previous
         // pass and are not now, or the reverse, add -+J J^T (after the first passes the pose barely moves: few flips).
-        const bool far = x.m > s_lc.lim_hi;  // outside for sure (false for NaN)
+        const bool far = (fabsf(u - lc.hu) > s_lc.hi_u) | (fabsf(v - lc.hv) > s_lc.hi_v);  // outside for sure (false for NaN)
         // padding slots (NaN inverse depth: never `far`) need no second look
         const int n_live = s_lc.n - 32 * word;
         const unsigned live_mask = n_live >= 32 ? 0xffffffffu : n_live <= 0 ? 0u : (1u << n_live) - 1u;
@@ -665,7 +676,7 @@ __device__ __forceinline__ double finish_entry(int t, const double* raw, const L
     if (t >= 8) {
         // H over the inside set = H_total (all candidates, per keyframe level) - H_outside; an empty inside set must give an
         // exactly zero H (the reference then fails its Cholesky, lm_optimizer.rs:131-133)
-        return raw[1] > 0.0 ? h_total[t - 8] - raw[13 + (t - 8)] : 0.0;
+        return raw[1] > 0.0 ? h_total[t - 8] - raw[kRawH + (t - 8)] : 0.0;
     }
     if (kSkew) return raw[t];
     const double* m = raw + 2;
@@ -673,9 +684,9 @@ __device__ __forceinline__ double finish_entry(int t, const double* raw, const L
     switch (t) {
         case 2: return fu * m[kSrp];
         case 3: return fv * m[kSrq];
-        case 4: return -m[kSrt];
-        case 5: return -(m[kSabp] + m[kSbbq]) * lc.inv_fy - fv * m[kSq];
-        case 6: return (m[kSaap] + m[kSabq]) * lc.inv_fx + fu * m[kSp];
+        case 4: return -m[kSrs];
+        case 5: return -m[kSbs] * lc.inv_fy - fv * m[kSq];
+        case 6: return m[kSas] * lc.inv_fx + fu * m[kSp];
         default: return (fv * lc.inv_fx) * m[kSaq] - (fu * lc.inv_fy) * m[kSbp];
     }
 }
@@ -714,7 +725,7 @@ __global__ void __maxnreg__(VORS_MAXREG) k_align(const AlignParams P) {
 __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignParams P) {
 #endif
     LmShared& S = lm_shared();
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int team = P.team;
     const int team_id = blockIdx.x / team, rank = blockIdx.x - team_id * team;
     const int n_teams = gridDim.x / team;
@@ -748,9 +759,10 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
         }
         __syncthreads();
 
-        for (int lvl = job.lvl_first; lvl >= job.lvl_last; --lvl) {
+        const int lvl_first = __shfl_sync(0xffffffffu, job.lvl_first, 0), lvl_last = __shfl_sync(0xffffffffu, job.lvl_last, 0);
+        for (int lvl = lvl_first; lvl >= lvl_last; --lvl) {
             const LevelJob& lj = job.lv[lvl];
-            const int n = *lj.n_ptr;
+            const int n = __shfl_sync(0xffffffffu, *lj.n_ptr, 0);
             const uint32_t* __restrict__ pts = lj.pts;
             const int n_stages = (n + kStageCand - 1) / kStageCand;
             const int TW = team * kWarps;
@@ -762,11 +774,12 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                 LevelConst c;
                 c.cx = k.cx;
                 c.cy = k.cy;
-                c.su = 2.0f / float(wm2i);
-                c.sv = 2.0f / float(hm2i);
-                const float eps = 2.0f * kBandPx / float(min(wm2i, hm2i));
-                c.lim_lo = 1.0f - eps;
-                c.lim_hi = 1.0f + eps;
+                c.hu = 0.5f * float(wm2i);
+                c.hv = 0.5f * float(hm2i);
+                c.lo_u = c.hu - kBandPx;
+                c.lo_v = c.hv - kBandPx;
+                c.hi_u = c.hu + kBandPx;
+                c.hi_v = c.hv + kBandPx;
                 c.wm2 = float(wm2i);
                 c.hm2 = float(hm2i);
                 c.zero_u = lj.zero_u;
@@ -801,11 +814,11 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
 #pragma unroll
                     for (int c = 0; c < 12; ++c) M[c] = S.M[c];
                     PassConst lc;
-                    lc.cx = s_lc.cx; lc.cy = s_lc.cy; lc.su = s_lc.su; lc.sv = s_lc.sv; lc.lim_lo = s_lc.lim_lo;
+                    lc.cx = s_lc.cx; lc.cy = s_lc.cy; lc.hu = s_lc.hu; lc.hv = s_lc.hv; lc.lo_u = s_lc.lo_u; lc.lo_v = s_lc.lo_v;
                     lc.magic_u = s_lc.magic_u; lc.magic_v = s_lc.magic_v; lc.rows = s_lc.rows; lc.img_biased = s_lc.img_biased;
                     lc.zero_u = s_lc.zero_u; lc.zero_v = s_lc.zero_v;
                     const Intrinsics k = s_lc.k;
-                    constexpr int kNumS = kHuber ? 27 : 11;  // per-thread sums besides the energy
+                    constexpr int kNumS = kHuber ? 27 : kNumMoments;  // per-thread sums besides the energy
                     const float huber_delta = s_lc.huber_delta;
                     Acc<kHuber> acc;
                     acc.e = 0.0f;
@@ -819,7 +832,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                     df.n_words = 0;
                     df.wlist = S.near_words[warp];
                     df.any_flip = 0;
-                    df.first_pass = S.init_phase;
+                    df.first_pass = __shfl_sync(0xffffffffu, S.init_phase, 0);
                     float* hs = S.hsm[tid];
                     const int gw = rank * kWarps + warp;
                     int n_slots = 0;
@@ -971,14 +984,14 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
 #endif
                     for (int v = lane; v < kNumRaw; v += 32) {
                         double s = 0.0;
-                        if (v < (kHuber ? 29 : 13)) {
+                        if (v < (kHuber ? 29 : kRawH)) {
 #pragma unroll
                             for (int w = 0; w < kWarps; ++w) s += double(S.warp_part[w][v]);
                         } else {
 #pragma unroll
                             for (int w = 0; w < kWarps; ++w) {
-                                s += S.hout[w][v - 13] + S.hout_pass[w][v - 13];  // hout: cumulative over the level's passes
-                                S.hout_pass[w][v - 13] = 0.0;
+                                s += S.hout[w][v - kRawH] + S.hout_pass[w][v - kRawH];  // hout: cumulative over the level's passes
+                                S.hout_pass[w][v - kRawH] = 0.0;
                             }
                         }
                         if (team > 1)
@@ -1044,10 +1057,10 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                     S.dbg[lvl][3] += 1;
                 }
 #endif
-                if (!S.cont) break;
+                if (!__shfl_sync(0xffffffffu, S.cont, 0)) break;
             }
 
-            if (job.pass_only) {
+            if (__shfl_sync(0xffffffffu, job.pass_only, 0)) {
                 if (writer && tid == 0) {
                     AlignResult& R = P.results[job_idx];
                     R.pass_n_inside = int(S.tot[1]);
@@ -1063,7 +1076,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                 R.energy[lvl] = S.keptE;
                 R.n_points[lvl] = n;
             }
-            const int failed = S.failed;
+            const int failed = __shfl_sync(0xffffffffu, S.failed, 0);
             if (tid == 0 && !failed) S.out_model = S.kept_model;  // inverse_compositional.rs:193
             __syncthreads();
             if (failed) break;  // inverse_compositional.rs:195-199

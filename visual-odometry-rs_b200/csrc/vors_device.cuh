@@ -34,7 +34,7 @@ constexpr int kChunk = 64;          // candidates per chunk-blocked record (768 
 constexpr int kPtAlign = VORS_STAGE_CHUNKS * kChunk;  // a level's candidate block is padded to this many candidates (one align-kernel ring stage)
 constexpr int kHStride = 24;         // doubles per (stream, level) in the H_total table (21 used)
 constexpr int kNumAcc = 29;          // finished pass: sum r^2, n_inside, g[6], H[21] (upper triangle)
-constexpr int kNumRaw = 34;          // raw pass accumulators: sum r^2, n_inside, 11 gradient moments (or g[6]), H_outside[21]
+constexpr int kNumRaw = 32;          // raw pass accumulators: sum r^2, n_inside, 9 gradient moments (or g[6]), H_outside[21]
 
 struct Geom {
     int L;
