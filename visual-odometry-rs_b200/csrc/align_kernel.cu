@@ -880,7 +880,10 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                             __syncwarp();  // orders these stores before lane 0's later stores to the same words
                         }
                         // the stage's far-bitmap words of the previous pass (one per lane 0..kStageWordsBm-1), fetched one iteration ahead
-                        unsigned old_next = (lane < kStageWordsBm && !df.first_pass && gw < n_stages) ? __ldcg(df.far + kStageWordsBm * gw + lane) : 0u;
+                        const bool far_lane = lane < kStageWordsBm && !df.first_pass;
+                        const unsigned* far_ptr = df.far + (kStageWordsBm * gw + lane);  // this lane's word of the stage being fetched
+                        const int far_step = kStageWordsBm * TW;
+                        unsigned old_next = (far_lane && gw < n_stages) ? __ldcg(far_ptr) : 0u;
                         for (int c = gw; c < n_stages; c += TW) {
                             // refill the slot freed by the previous iteration (every lane consumed its loads before that
                             // iteration's trailing __syncwarp) with the stage kStages - 1 ahead
@@ -894,7 +897,8 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                             mbar_wait(bar_base + ring_slot * 8u, ring_parity);  // TMA bytes have landed
                             const unsigned old_words = old_next;
                             const unsigned old_nz = __ballot_sync(0xffffffffu, old_words != 0u);
-                            if (lane < kStageWordsBm && !df.first_pass && c + TW < n_stages) old_next = __ldcg(df.far + kStageWordsBm * (c + TW) + lane);
+                            far_ptr += far_step;
+                            if (far_lane && c + TW < n_stages) old_next = __ldcg(far_ptr);
                             const float* sp = &S.ring[warp][ring_slot * kStageWords] + lane;
                             // word j of the stage = 32 consecutive candidates (chunk j / 2, half j % 2), one per lane
 #define VORS_STEP(CH, HALF, FNEW, FOLD)                                                               \
