@@ -4,12 +4,12 @@
 // walks the pyramid coarse to fine and, per level, runs the reference's Levenberg-Marquardt loop
 // (src/math/optimizer.rs:57-70 + src/core/track/lm_optimizer.rs:113-192) entirely on the device:
 //
-//   pass      every warp streams its share of the level's candidate records (12 B per candidate, 128 candidates per
+//   pass      every warp streams its share of the level's candidate records (12 B per candidate, 256 candidates per
 //             stage) through its own shared-memory ring with TMA bulk copies (cp.async.bulk, SASS UBLKCP) issued
 //             kStages - 1 stages ahead, so HBM latency is covered by bytes in flight instead of by occupancy, and
-//             evaluates four candidates per lane per stage, branch-free on the common path: warp with the folded
+//             evaluates eight candidates per lane per stage, branch-free on the common path: warp with the folded
 //             3x4 matrix of lie.cuh (lm_optimizer.rs:213-219), inside test with a safety margin, f32 bilinear sample
-//             of u8 texels (lm_optimizer.rs:227-251), residual against the template value, sum r^2 and eleven
+//             of u8 texels (lm_optimizer.rs:227-251), residual against the template value, sum r^2 and nine
 //             moments of (gu r, gv r) from which g = sum J r is assembled once per pass (inverse_compositional.rs:
 //             313-341; J itself is never formed on the common path).  Candidates that fall outside read a zero page
 //             (exact zero contributions) and add J J^T to per-thread shared-memory sums: H over the inside set is
@@ -18,14 +18,14 @@
 //             reference's own operation order (eval_energy + compute_eval_data, lm_optimizer.rs:68-107, fused);
 //   reduce    warp shuffles -> shared memory -> f64 per-CTA partials -> (team > 1) peer partials
 //             through global memory with one counter barrier per pass; fixed order => deterministic;
-//   decide    thread 0 of every CTA redundantly replays accept / reject / stop (lm_optimizer.rs:
+//   decide    the last warp of every CTA redundantly replays accept / reject / stop (lm_optimizer.rs:
 //             140-192), damps, solves the 6x6 system by Cholesky, applies se3::exp and the first
 //             order renormalisation (lm_optimizer.rs:123-136, 198-209) and publishes the next
 //             candidate model's warp matrix; no host round trip anywhere in the loop.
 //
 // team == 1 is the throughput configuration (one alignment per CTA, two CTAs per SM so one CTA's
 // serial solve overlaps the other's pass); team > 1 trades efficiency for latency on few streams.
-// No tensor cores: the work is ~90 scalar f32 instructions per 12-byte candidate, bounded by
+// No tensor cores: the work is ~80 scalar instructions per 12-byte candidate, bounded by
 // instruction issue, not by a dense contraction.
 #include <cooperative_groups.h>
 #include <cstdio>
@@ -136,8 +136,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     } while (!done);
 }
 
-// int -> float conversions: I2F on the XU pipe (measured: the ALU pipe is the busier one in this kernel, so the
-// 2-ALU-op magic-number conversion is only used where it fuses with work that is needed anyway).
+// int -> float conversions: one I2FP each (the loop is issue-bound: the two-instruction 2^23 magic-number conversion
+// only pays where it fuses with work that is needed anyway, i.e. the floor of the warped coordinates).
 __device__ __forceinline__ float u2f(uint32_t v) { return float(v); }
 // 1/x: MUFU.RCP seed + one Newton step (2 FMAs) = correctly rounded to within 1 ulp without the slow-path range
 // checks of an IEEE division; x = 0 / inf / NaN give inf / NaN, which the inside test rejects like the reference.
@@ -476,7 +476,6 @@ struct FrontA {
     bool ok;  // inside for sure (false for NaN)
 };
 __device__ __forceinline__ FrontA front_a(uint32_t pk, float rho, uint32_t gr, const float (&M)[12], const PassConst& lc) {
-    // int -> float through the 2^23 magic number: one LOP3 (ALU pipe) + one FADD (FMA pipe) instead of mask + I2F
 #if VORS_X_MAGIC
     const float x = __uint_as_float((pk & 0xFFFu) | 0x4B000000u) - 8388608.0f;
 #else

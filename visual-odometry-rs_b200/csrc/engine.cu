@@ -239,7 +239,7 @@ class Engine {
         if (info.max_resident_ctas < 1) return fail(VORS_E_CUDA, "align kernel cannot be resident on this device");
 
         const size_t N = size_t(n), P = size_t(g.pix_stride), I = size_t(rows) * cols, PT = size_t(g.pt_total);
-        // + slack: the align kernel prefetches image lines up to one team-stride of stages past a texel
+        // + slack past the last slab (zero page reads of the last stream stay inside the allocation with room to spare)
         CU_TRY(cudaMalloc(&d_pyr, N * P + (size_t(1) << 20)));
         CU_TRY(cudaMemsetAsync(d_pyr, 0, N * P + (size_t(1) << 20), L.stream));  // the zero page of every slab stays zero: no kernel writes it
         CU_TRY(cudaMalloc(&d_stage8, N * I));
