@@ -401,9 +401,16 @@ def run_reference(args):
 
 def main():
     args = parse_args()
+    # stdout carries exactly one JSON line: anything a library writes to fd 1 meanwhile (NCCL prints its version banner
+    # there when NCCL_DEBUG is set) goes to stderr instead
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
     out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    sys.stdout.flush()
     if out is not None:
-        print(json.dumps(out))
+        os.write(result_fd, (json.dumps(out) + "\n").encode())
+    os.close(result_fd)
 
 
 if __name__ == "__main__":
