@@ -316,7 +316,7 @@ def run_ours(args):
                                         "keyframe_ms": kf_ms / K}},
         }
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline_port(gray_h, depth_h, kw, n_streams=3, n_frames=F)
+            out["cpu_baseline"] = cpu_baseline_port(gray_h, depth_h, kw, n_streams=9, n_frames=F)  # ~10 s of CPU work
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
