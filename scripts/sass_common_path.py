@@ -41,7 +41,8 @@ def main():
         if m and int(m.group(2), 16) < a:
             t = int(m.group(2), 16)
             body = [y for (b, y) in ins if t <= b <= a]
-            if sum("LDG.E.U8" in y for y in body) == 32 and any("UBLKCP" in y for y in body):
+            gathers = sum("LDG.E.U8" in y for y in body), sum("TLD4" in y for y in body)
+            if gathers in ((32, 0), (0, 8)) and any("UBLKCP" in y for y in body):  # byte loads, or -DVORS_TEX=1: one gather each
                 loops.append((a - t, t, a))
     _, head, tail = min(loops)
     start, end = at[head], at[tail]
