@@ -1,21 +1,23 @@
 #!/usr/bin/env python
-"""bench.py — RGB-D frames aligned / s at 640x480, 5 pyramid levels (BASELINE.json metric).
+"""bench.py — RGB-D frames aligned / s (BASELINE.json metric), with the oracle inside the benchmarked path.
 
-Workload (BASELINE.json configs[1]): per GPU, B independent synthetic 640x480
+Default workload = BASELINE.json configs[1]: per GPU, B independent synthetic 640x480
 RGB-D streams, dense candidates (every pixel with depth != 0), 5 levels, 10 fixed LM rounds per level
 (11 energy passes / level), Tracker semantics (keyframe switch when the optical flow reaches 1 px).
 One step = every stream tracks its next frame = B alignments in ONE persistent kernel launch.
+`--config {1,3,4,5}` runs the other BASELINE configs through the same code (table `CONFIGS`).
 
-  value   frames/s with the step's inputs already resident in HBM (vors_batch_track_device)
+  value   frames/s with the step's inputs already resident in HBM (vors_batch_track_device_next)
   e2e     frames/s through the C ABI with HOST buffers (vors_batch_track_next: every call announces the next step's frames
-          so that their upload overlaps the alignment): pinned row-major frames in,
-          poses out, H2D/D2H copies inside the timed region
-  roofline   align kernel: algorithmic bytes (10 B per candidate-pass) / its device time
-  cpu_baseline  the C++ oracle (a restatement of the reference's algorithm, not rustc output), 1 core,
-          on a bounded sample of the same streams
+          so that their upload overlaps the alignment): pinned row-major frames in, poses out, H2D/D2H inside the timed region
+  roofline   align kernel: algorithmic bytes (10 B per candidate-pass dense, 17 B sparse) / its device time
+  parity_in_run   the poses both arms produced for the first streams, at EVERY step of the run (warm-up included), against
+          the CPU oracle's parity build tracking the same frames; the run fails (exit code 3) above 1e-4 rad / 1e-4 m
+  cpu_baseline  the C++ oracle (a restatement of the reference's algorithm, not rustc output), 1 core, bounded sample
   --impl reference   the same oracle on all host cores (independent streams, one per thread)
 
-Launch: python bench.py --gpus N --steps K --warmup W   (N>1: torchrun, one rank per GPU, NCCL pose gather)
+Launch: python bench.py --gpus N --steps K --warmup W   (N>1: torchrun, one rank per GPU; the only exchange is an
+asynchronous NCCL all-gather of 32-byte pose records per step, off the critical path)
 """
 import argparse
 import ctypes as C
@@ -32,12 +34,27 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "visual-odometry-rs_b200"))
 
-ROWS, COLS, LEVELS, FIXED_ITERS = 480, 640, 5, 10
-METRIC = "RGB-D frames aligned/sec at 640x480, 5 pyramid levels"
-WORKLOAD = ("configs[1]: 640x480 synthetic RGB-D sequences, dense (all-pixel) candidates, 5 levels, "
-            "10 fixed LM rounds/level, Tracker semantics incl. keyframe switches")
-MAX_FRAMES = 12  # distinct synthetic frames rendered per stream
-ALGO_BYTES_PER_POINT_PASS = 10.0  # idepth 4 + template 1 + gradient pair 4 + image texel 1
+C2F, DENSE, DSO = 0, 1, 2
+# BASELINE.json `configs` (index + 1) -> workload.  `streams`: independent RGB-D streams per GPU; `bytes`: algorithmic
+# bytes per candidate-pass of the align kernel (10 dense, 17 sparse); `frames`: distinct rendered frames.
+CONFIGS = {
+    1: dict(rows=480, cols=640, levels=5, mode=C2F, fixed_iters=0, streams=1, frames=12, bytes=17.0,
+            text="configs[0]: one 640x480 synthetic RGB-D stream, coarse-to-fine candidates (threshold 7), 5 levels, "
+                 "reference-adaptive LM: single-alignment latency"),
+    2: dict(rows=480, cols=640, levels=5, mode=DENSE, fixed_iters=10, streams=296, frames=12, bytes=10.0,
+            text="configs[1]: 640x480 synthetic RGB-D sequences, dense (all-pixel) candidates, 5 levels, "
+                 "10 fixed LM rounds/level, Tracker semantics incl. keyframe switches"),
+    3: dict(rows=960, cols=1280, levels=6, mode=DSO, fixed_iters=0, streams=148, frames=6, bytes=17.0,
+            text="configs[2]: 1280x960 synthetic RGB-D sequences, DSO candidates at level 0 (target 2000) propagated up "
+                 "the inverse-depth pyramid, 6 levels, reference-adaptive LM"),
+    4: dict(rows=480, cols=640, levels=5, mode=DENSE, fixed_iters=10, streams=1, frames=12, bytes=10.0,
+            text="configs[3]: one independent 640x480 keyframe->frame alignment per GPU (dense, 5 levels, 10 fixed LM "
+                 "rounds/level), pose all-gather"),
+    5: dict(rows=1080, cols=1920, levels=6, mode=C2F, fixed_iters=0, streams=148, frames=6, bytes=17.0,
+            text="configs[4]: 1920x1080 synthetic RGB-D streams, coarse-to-fine (semi-dense) candidates, threshold 7, "
+                 "6 levels, reference-adaptive LM (the shape src/bin/vors_track.rs:34-40 runs)"),
+}
+PARITY_TOL_RAD, PARITY_TOL_M = 1e-4, 1e-4  # north_star: pose within 1e-4 rad / 1e-4 m of the reference
 
 
 def parse_args():
@@ -46,10 +63,17 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=296, help="independent RGB-D streams per GPU (2 CTAs x 148 SMs)")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs index + 1 (default 2 = configs[1])")
+    ap.add_argument("--streams", type=int, default=0, help="independent RGB-D streams per GPU (0 = the config's default; 296 = 2 CTAs x 148 SMs)")
     ap.add_argument("--team", type=int, default=0, help="CTAs per alignment (0 = auto)")
+    ap.add_argument("--parity-streams", type=int, default=8, help="streams whose poses are checked against the oracle at every step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip parity_in_run (A/B timing runs only; the line then says so)")
     return ap.parse_args()
+
+
+def metric_name(cfg):
+    return f"RGB-D frames aligned/sec at {cfg['cols']}x{cfg['rows']}, {cfg['levels']} pyramid levels"
 
 
 def dist_env():
@@ -115,18 +139,19 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_streams(n_streams, n_frames, seed0, device):
+def make_streams(cfg, n_streams, n_frames, seed0, device):
     """Per stream: its own textured-plane scene and smooth trajectory.  Returns torch tensors
-    gray u8 [n_frames, n_streams, ROWS, COLS], depth u16 (same shape), gt poses [n_frames, n_streams, 7], scene0."""
+    gray u8 [n_frames, n_streams, rows, cols], depth u16 (same shape), gt poses [n_frames, n_streams, 7], scene0."""
     import torch
     from vors_b200 import synth
 
-    gray = torch.empty((n_frames, n_streams, ROWS, COLS), dtype=torch.uint8, device=device)
-    depth = torch.empty((n_frames, n_streams, ROWS, COLS), dtype=torch.uint16, device=device)
+    rows, cols = cfg["rows"], cfg["cols"]
+    gray = torch.empty((n_frames, n_streams, rows, cols), dtype=torch.uint8, device=device)
+    depth = torch.empty((n_frames, n_streams, rows, cols), dtype=torch.uint16, device=device)
     gt = np.zeros((n_frames, n_streams, 7))
     scene0 = None
     for s in range(n_streams):
-        scene = synth.make_scene(seed0 + s, ROWS, COLS)
+        scene = synth.make_scene(seed0 + s, rows, cols)
         scene0 = scene0 or scene
         poses = synth.trajectory(seed0 + s, n_frames)
         g, d = synth.render_batch_torch(scene, poses, device, frame_seed=s, chunk=n_frames)
@@ -141,13 +166,21 @@ def ptr_array(base_ptr, n, stride_bytes):
     return (C.c_void_p * n)(*[base_ptr + i * stride_bytes for i in range(n)])
 
 
+def tracker_kwargs(cfg, scene):
+    from vors_b200 import synth
+
+    return dict(nb_levels=cfg["levels"], candidate_mode=cfg["mode"], fixed_iters=cfg["fixed_iters"], **synth.scene_config_kwargs(scene))
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     import vors_b200 as vb
-    from vors_b200 import synth
+    from vors_b200 import shard
 
+    cfg = CONFIGS[args.config]
+    rows, cols = cfg["rows"], cfg["cols"]
     rank, world, local = dist_env()
     assert torch.cuda.is_available(), "bench.py (impl=ours) needs a GPU: libvors_b200 has no CPU fallback"
     torch.cuda.set_device(local)
@@ -156,17 +189,18 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     if not os.path.exists(vb.LIB_PATH):
         raise SystemExit(f"{vb.LIB_PATH} missing: run __graft_entry__.build() first")
+    binfo = vb.build_info()
 
-    B, K, W = args.streams, args.steps, args.warmup
+    B, K, W = args.streams or cfg["streams"], args.steps, args.warmup
     T = K + W
-    # At most MAX_FRAMES distinct frames per stream are rendered (3.3 GB of device and of pinned host memory at 296 streams);
-    # longer runs walk the rendered trajectory back and forth, so consecutive steps always see adjacent frames.
-    F = min(T, MAX_FRAMES - 1)
+    # At most cfg["frames"] distinct frames per stream are rendered (device + pinned host memory); longer runs walk the
+    # rendered trajectory back and forth, so consecutive steps always see adjacent frames.
+    F = min(T, cfg["frames"] - 1)
     def fi(k):
         m = k % (2 * F)
         return m if m <= F else 2 * F - m
     t0 = time.time()
-    gray, depth, gt, scene = make_streams(B, F + 1, 100000 * (rank + 1), device)
+    gray, depth, gt, scene = make_streams(cfg, B, F + 1, 100000 * (rank + 1), device)
     # device-resident inputs in the library's internal layout (column-major per frame)
     gray_cm = gray.transpose(-1, -2).contiguous()
     depth_cm = depth.transpose(-1, -2).contiguous()
@@ -177,29 +211,36 @@ def run_ours(args):
     depth_h.copy_(depth)
     torch.cuda.synchronize()
     gen_s = time.time() - t0
-    I = ROWS * COLS
+    I = rows * cols
 
-    kw = dict(nb_levels=LEVELS, candidate_mode=vb.CANDIDATES_DENSE, fixed_iters=FIXED_ITERS, device=local,
-              team_size=args.team, **synth.scene_config_kwargs(scene))
-    cfg = vb.Config(**kw)
+    kw = dict(device=local, team_size=args.team, **tracker_kwargs(cfg, scene))
+    vcfg = vb.Config(**kw)
 
     ts = [np.full(B, float(k)) for k in range(T + 1)]
     status = np.zeros(B, np.int32)
     stats = (vb.TrackStats * B)()
-    from vors_b200 import shard
+    P = 0 if args.no_parity else min(args.parity_streams, B)
 
-    def gather_poses(bt):
-        """Streams shard across ranks with no data-path collective; the only exchange is this all-gather of 32-byte
-        pose records (NCCL), once per step."""
-        if world > 1:
-            _, p = bt.current_frames()
-            return shard.gather_poses(shard.pack_records(p, status), B * world, device=device)
-        return None
+    # Streams shard across ranks with no data-path collective; the only exchange is one all-gather of 32-byte pose records
+    # per step.  It is asynchronous: submitted after step k, it completes while step k + 1 runs; collected one step late.
+    pg = shard.PoseGatherer(B * world, device=device, depth=2) if world > 1 else None
+    gathered = [0]
+    def exchange(bt):
+        if pg is None:
+            return
+        if pg.in_flight() == pg.depth:
+            pg.collect()
+            gathered[0] += 1
+        _, p = bt.current_frames()
+        pg.submit(p, status)
+    def drain():
+        while pg is not None and pg.in_flight():
+            last = pg.collect()
+            gathered[0] += 1
+            assert last.shape == (B * world, shard.POSE_RECORD_FLOATS)
 
     def new_tracker():
-        g0 = gray_h[0].numpy()
-        d0 = depth_h[0].numpy()
-        return vb.BatchTracker(cfg, ts[0], d0, ts[0], g0, layout=vb.ROW_MAJOR)
+        return vb.BatchTracker(vcfg, ts[0], depth_h[0].numpy(), ts[0], gray_h[0].numpy(), layout=vb.ROW_MAJOR)
 
     def barrier():
         if world > 1:
@@ -214,6 +255,10 @@ def run_ours(args):
         return x
 
     sampler = ClockSampler(local)
+    poses_log = {"device": np.zeros((T + 1, P, 7), np.float32), "e2e": np.zeros((T + 1, P, 7), np.float32)}
+    def log_poses(arm, bt, k):
+        if P:
+            poses_log[arm][k] = bt.current_frames()[1][:P]
 
     # ---- arm 1: inputs resident in HBM ------------------------------------------------------------------
     bt = new_tracker()
@@ -223,7 +268,8 @@ def run_ours(args):
                                status.ctypes.data, C.addressof(stats), gray_cm[fi(k + 1)].data_ptr() if k < T else None)
     for k in range(1, W + 1):
         step_device(k)
-        gather_poses(bt)
+        exchange(bt)
+        log_poses("device", bt, k)
     align_ms = pyr_ms = kf_ms = up_ms = 0.0
     launches = point_passes = switches = failed = 0
     barrier()
@@ -232,13 +278,15 @@ def run_ours(args):
     t_start = time.perf_counter()
     for k in range(W + 1, T + 1):
         step_device(k)
-        gather_poses(bt)
+        exchange(bt)
+        log_poses("device", bt, k)
         tm = bt.last_timing()
         align_ms += tm["align_ms"]; pyr_ms += tm["pyramid_ms"]; kf_ms += tm["keyframe_ms"]; up_ms += tm["upload_ms"]
         l, pp = bt.last_counters()
         launches += l; point_passes += pp
         switches += sum(s.keyframe_changed for s in stats)
         failed += int((status != 0).sum())
+    drain()
     barrier()
     dev_s = max_over_ranks(time.perf_counter() - t_start)
     clocks = sampler.stop() if rank == 0 else None
@@ -255,15 +303,17 @@ def run_ours(args):
     nxt = lambda k: img_ptrs[fi(k + 1)] if k < T else None
     for k in range(1, W + 1):
         bt.track_raw(ts[k].ctypes.data, dep_ptrs[fi(k)], ts[k].ctypes.data, img_ptrs[fi(k)], status.ctypes.data, C.addressof(stats), nxt(k))
-        gather_poses(bt)
+        exchange(bt)
+        log_poses("e2e", bt, k)
     e2e_switches = 0
     barrier()
     t_start = time.perf_counter()
     for k in range(W + 1, T + 1):
         bt.track_raw(ts[k].ctypes.data, dep_ptrs[fi(k)], ts[k].ctypes.data, img_ptrs[fi(k)], status.ctypes.data, C.addressof(stats), nxt(k))
-        bt.current_frames()  # device -> host read of the step's result (poses) is part of the call above; this is the accessor
-        gather_poses(bt)
+        exchange(bt)  # device -> host read of the step's result (poses) happens inside the call above
+        log_poses("e2e", bt, k)
         e2e_switches += sum(s.keyframe_changed for s in stats)
+    drain()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t_start)
     _, poses_b = bt.current_frames()
@@ -280,28 +330,33 @@ def run_ours(args):
     rot_err, trans_err = err(poses_a)
 
     out = None
+    parity = None
     if rank == 0:
         peak, peak_src = peaks()
-        algo_bytes = ALGO_BYTES_PER_POINT_PASS * point_passes  # rank 0's launches
+        algo_bytes = cfg["bytes"] * point_passes  # rank 0's launches
         achieved = algo_bytes / (align_ms * 1e-3) / 1e9 if align_ms > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "align_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and args.config == 2:
             try:
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         out = {
-            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": metric_name(cfg), "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_s / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "streams_per_gpu": B, "frames_per_step": B * world,
-                       "inputs": f"larger than L2: {B * 12.3e-3:.1f} GB of per-stream keyframe+frame data touched per step",
+            "config": {"workload": cfg["text"], "streams_per_gpu": B, "frames_per_step": B * world,
+                       "inputs": f"larger than L2: {B * I * (cfg['bytes'] + 3) * 1.33 / 1e9:.2f} GB of per-stream keyframe+frame data touched per step"
+                                 if B * I * 13 > 126e6 else "one stream per GPU: the working set fits L2 (latency configuration)",
                        "frames": f"{F + 1} rendered frames per stream, walked back and forth",
                        "team_size": args.team or "auto", "keyframe_switches_per_step": switches / K,
-                       "failed_alignments": failed, "pose_gather": "NCCL all_gather per step" if world > 1 else "none (1 GPU)",
+                       "failed_alignments": failed,
+                       "pose_gather": (f"async NCCL all_gather_into_tensor per step, {gathered[0]} exchanges collected one step late"
+                                       if world > 1 else "none (1 GPU)"),
                        "max_pose_error_vs_ground_truth": {"rad": rot_err, "m": trans_err},
-                       "arms_max_abs_pose_diff": float(np.max(np.abs(poses_a - poses_b))), "synth_seconds": gen_s},
+                       "arms_max_abs_pose_diff": float(np.max(np.abs(poses_a - poses_b))), "synth_seconds": gen_s,
+                       "library": binfo},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_s / K * 1e3,
                     "h2d_bytes_per_step": B * I + (e2e_switches / K) * I * 2 + B * 28,
@@ -310,17 +365,24 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_align (persistent LM alignment)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_point_pass": cfg["bytes"],
                          "algorithmic_bytes_per_launch": algo_bytes / K, "avg_launch_ms": align_ms / K,
                          "point_passes_per_launch": point_passes / K,
                          "step_share": {"upload_ms": up_ms / K, "pyramid_ms": pyr_ms / K, "align_ms": align_ms / K,
                                         "keyframe_ms": kf_ms / K}},
         }
+        if P:
+            parity = parity_in_run(cfg, gray_h, depth_h, kw, P, T, fi, poses_log)
+            out["parity_in_run"] = parity
+        else:
+            out["parity_in_run"] = {"ok": None, "note": "skipped (--no-parity): timing-only run, no parity claim"}
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline_port(gray_h, depth_h, kw, n_streams=9, n_frames=F)  # ~10 s of CPU work
+            n_s = max(1, min(9, B))
+            out["cpu_baseline"] = cpu_baseline_port(gray_h, depth_h, kw, n_streams=n_s, n_frames=F)  # ~10 s of CPU work
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    return out
+    return out, (parity is None or bool(parity["ok"]))
 
 
 def oracle_cfg(kw):
@@ -328,6 +390,51 @@ def oracle_cfg(kw):
 
     kw = {k: v for k, v in kw.items() if k not in ("device", "team_size")}
     return O.default_config(**kw)
+
+
+def parity_in_run(cfg, gray_h, depth_h, kw, n_streams, T, fi, poses_log):
+    """The oracle INSIDE the benchmarked path: the CPU oracle's parity build (-O2 -ffp-contract=off, the reference's
+    sequential f32 sums) tracks the very frames the two GPU arms were given, for the first `n_streams` streams and every
+    step of the run (warm-up + timed), one stream per host thread; pose differences are taken after every step."""
+    import concurrent.futures as cf
+
+    from oracle import oracle_py as O
+
+    O.build()
+    ocfg = oracle_cfg(kw)
+    t0 = time.perf_counter()
+
+    def one(s):
+        tr = O.Tracker(ocfg, 0.0, depth_h[0, s].numpy(), 0.0, gray_h[0, s].numpy(), fast=False)
+        out = np.zeros((T + 1, 7), np.float32)
+        sw = 0
+        for k in range(1, T + 1):
+            _, st, _ = tr.track(float(k), depth_h[fi(k), s].numpy(), float(k), gray_h[fi(k), s].numpy())
+            sw += st.keyframe_changed
+            out[k] = tr.current_frame()[1].as_array()
+        return out, sw
+
+    with cf.ThreadPoolExecutor(max_workers=min(n_streams, os.cpu_count() or 1)) as pool:
+        res = list(pool.map(one, range(n_streams)))
+    oracle_poses = np.stack([r[0] for r in res], 1)  # [T+1, P, 7]
+    worst = {}
+    for arm, gp in poses_log.items():
+        mr = mm = 0.0
+        for k in range(1, T + 1):
+            for s in range(n_streams):
+                a, m = O.pose_error(gp[k, s], oracle_poses[k, s])
+                mr, mm = max(mr, a), max(mm, m)
+        worst[arm] = (mr, mm)
+    max_rad = max(v[0] for v in worst.values())
+    max_m = max(v[1] for v in worst.values())
+    return {"streams": n_streams, "frames": T, "alignments_compared": 2 * n_streams * T,
+            "max_rad": max_rad, "max_m": max_m, "tol_rad": PARITY_TOL_RAD, "tol_m": PARITY_TOL_M,
+            "ok": bool(max_rad <= PARITY_TOL_RAD and max_m <= PARITY_TOL_M),
+            "per_arm": {a: {"max_rad": v[0], "max_m": v[1]} for a, v in worst.items()},
+            "oracle_keyframe_switches": int(sum(r[1] for r in res)),
+            "oracle": "C++ restatement, parity build (-O2 -ffp-contract=off), the reference's sequential f32 accumulation; "
+                      "compared after every step of both arms (device-resident and host/announced)",
+            "seconds": time.perf_counter() - t0}
 
 
 def cpu_baseline_port(gray_h, depth_h, kw, n_streams, n_frames):
@@ -345,9 +452,13 @@ def cpu_baseline_port(gray_h, depth_h, kw, n_streams, n_frames):
             tr.track(float(k), d, float(k), g)
             total += time.perf_counter() - t0
             frames += 1
+            if total > 25.0:
+                break
+        if total > 25.0:
+            break
     return {"value": frames / total, "unit": "frames/s", "cores": 1, "kind": "port",
-            "sample": f"{n_streams} streams x {n_frames} frames of the same workload (Tracker::track only, PNG decode excluded); "
-                      "C++ restatement of the reference algorithm, not rustc output", "seconds": total}
+            "sample": f"{frames} frames of the same workload on up to {n_streams} of its streams (Tracker::track only, PNG decode "
+                      "excluded); C++ restatement of the reference algorithm, not rustc output", "seconds": total}
 
 
 def run_reference(args):
@@ -359,28 +470,32 @@ def run_reference(args):
     import concurrent.futures as cf
 
     from oracle import oracle_py as O
-    from vors_b200 import synth
 
+    cfg = CONFIGS[args.config]
     O.build()
     cores = os.cpu_count() or 1
     K, W = args.steps, args.warmup
     T = K + W
+    F = min(T, cfg["frames"] - 1)
+    def fi(k):
+        m = k % (2 * F)
+        return m if m <= F else 2 * F - m
     try:
         import torch
         device = torch.device("cuda", local) if torch.cuda.is_available() else torch.device("cpu")
     except Exception:
         device = None
     n = cores
-    gray, depth, gt, scene = make_streams(n, T + 1, 100000, device)
+    gray, depth, gt, scene = make_streams(cfg, n, F + 1, 100000, device)
     gray = gray.cpu().numpy()
     depth = depth.cpu().numpy()
-    kw = dict(nb_levels=LEVELS, candidate_mode=1, fixed_iters=FIXED_ITERS, **synth.scene_config_kwargs(scene))
-    cfg = oracle_cfg(kw)
-    trackers = [O.Tracker(cfg, 0.0, depth[0, s], 0.0, gray[0, s], fast=True) for s in range(n)]
+    kw = tracker_kwargs(cfg, scene)
+    ocfg = oracle_cfg(kw)
+    trackers = [O.Tracker(ocfg, 0.0, depth[0, s], 0.0, gray[0, s], fast=True) for s in range(n)]
     pool = cf.ThreadPoolExecutor(max_workers=cores)
 
     def step(k):
-        list(pool.map(lambda s: trackers[s].track(float(k), depth[k, s], float(k), gray[k, s]), range(n)))
+        list(pool.map(lambda s: trackers[s].track(float(k), depth[fi(k), s], float(k), gray[fi(k), s]), range(n)))
 
     for k in range(1, W + 1):
         step(k)
@@ -389,10 +504,13 @@ def run_reference(args):
         step(k)
     secs = time.perf_counter() - t0
     value = n * K / secs
-    return {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
-            "ms_per_step": secs / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD, "streams": n, "note": "each step = one frame on each of `cores` independent streams"},
+    return {"impl": "reference", "metric": metric_name(cfg), "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": K,
+            "warmup": W, "ms_per_step": secs / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["text"], "streams_per_gpu": args.streams or cfg["streams"],
+                       "frames_per_step": (args.streams or cfg["streams"]) * args.gpus, "sampled_streams": n,
+                       "note": "bounded sample of the workload: each timed step = one frame on each of `cores` of its streams "
+                               "(one per host thread); value = sampled frames / second"},
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
                              "sample": f"{n} independent streams x {K} timed frames, one stream per thread; C++ restatement "
                                        "of the reference algorithm (-O3), not rustc output"},
@@ -406,11 +524,18 @@ def main():
     sys.stdout.flush()
     result_fd = os.dup(1)
     os.dup2(2, 1)
-    out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    ok = True
+    if args.impl == "reference":
+        out = run_reference(args)
+    else:
+        out, ok = run_ours(args)
     sys.stdout.flush()
     if out is not None:
         os.write(result_fd, (json.dumps(out) + "\n").encode())
     os.close(result_fd)
+    if not ok:
+        print("bench.py: parity_in_run FAILED: GPU poses differ from the oracle by more than 1e-4 rad / 1e-4 m", file=sys.stderr)
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -119,6 +119,9 @@ typedef struct vors_track_stats {
 void vors_config_default(vors_config* cfg);
 const char* vors_last_error(void);
 const char* vors_version(void);
+/* "src=<sha256/16 of the CUDA sources and headers the library was compiled from> built=<UTC time> arch=sm_100a":
+ * lets a caller (and __graft_entry__.build() / smoke()) prove which sources the loaded binary came from. */
+const char* vors_build_info(void);
 /* Number of usable sm_100 devices (0 when none; never fails). */
 int vors_device_count(void);
 
@@ -188,6 +191,9 @@ int vors_batch_last_timing(const vors_batch* b, float ms[4]);
 /* Kernel launches issued by the last track call and the sum of candidate-point evaluations
  * (points x passes) the align kernel executed — feeds bench.py's roofline. */
 int vors_batch_last_counters(const vors_batch* b, uint64_t* launches, uint64_t* point_passes);
+/* Shape of the last align launch: CTAs cooperating on one alignment (`team`; 1 = the throughput configuration chosen when
+ * the batch fills the device) and alignments in flight at once (`n_teams`). */
+int vors_batch_last_launch_shape(const vors_batch* b, int* team, int* n_teams);
 int vors_batch_set_tracing(vors_batch* b, int enabled);
 int vors_batch_last_trace(const vors_batch* b, uint32_t stream, vors_trace_rec* out, int cap, int* len);
 void vors_batch_destroy(vors_batch* b);

@@ -38,7 +38,16 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     idx = shard.partition(N_STREAMS, rank, world)
-    full = shard.gather_poses(_track_streams(oracle_py, idx), N_STREAMS)
+    local = _track_streams(oracle_py, idx)
+    full = shard.gather_poses(local, N_STREAMS)
+    # the asynchronous, preallocated form used by bench.py: two exchanges in flight, collected in submission order
+    pg = shard.PoseGatherer(N_STREAMS, device="cpu", depth=2)
+    pg.submit(local[:, :7], local[:, 7])
+    pg.submit(local[:, :7] + 1.0, local[:, 7])
+    a, b = pg.collect(), pg.collect()
+    assert pg.in_flight() == 0
+    assert np.array_equal(a, full), "PoseGatherer differs from gather_poses"
+    assert np.array_equal(b[:, :7], full[:, :7] + 1.0) and np.array_equal(b[:, 7], full[:, 7])
     q.put((rank, full))
     dist.barrier()
     dist.destroy_process_group()
@@ -68,3 +77,14 @@ def test_two_rank_gloo_gather_matches_single_process(oracle):
     assert np.array_equal(results[0], results[1])  # every rank holds the same gathered table
     assert np.array_equal(results[0], single)      # in global stream order, identical to the unsharded run
     assert results[0].shape == (N_STREAMS, 8) and np.all(results[0][:, 7] == 0)
+
+
+def test_pose_gatherer_single_process_is_identity():
+    pg = shard.PoseGatherer(7, device="cpu")
+    poses = np.arange(49, dtype=np.float32).reshape(7, 7)
+    status = np.arange(7, dtype=np.int32) % 2
+    pg.submit(poses, status)
+    out = pg.collect()
+    assert np.array_equal(out[:, :7], poses) and np.array_equal(out[:, 7], status.astype(np.float32))
+    with pytest.raises(RuntimeError):
+        pg.collect()

@@ -91,6 +91,7 @@ SIGNATURES = {
     "vors_config_default": (None, [_P(ConfigStruct)]),
     "vors_last_error": (C.c_char_p, []),
     "vors_version": (C.c_char_p, []),
+    "vors_build_info": (C.c_char_p, []),
     "vors_device_count": (C.c_int, []),
     "vors_tracker_create": (C.c_int, [_P(ConfigStruct), C.c_double, _vp, C.c_double, _vp, C.c_uint32, C.c_uint32, C.c_int, _P(_vp)]),
     "vors_tracker_track": (C.c_int, [_vp, C.c_double, _vp, C.c_double, _vp, _P(TrackStats)]),
@@ -108,6 +109,7 @@ SIGNATURES = {
     "vors_batch_size": (C.c_int, [_vp]),
     "vors_batch_last_timing": (C.c_int, [_vp, _P(C.c_float)]),
     "vors_batch_last_counters": (C.c_int, [_vp, _P(C.c_uint64), _P(C.c_uint64)]),
+    "vors_batch_last_launch_shape": (C.c_int, [_vp, _P(C.c_int), _P(C.c_int)]),
     "vors_batch_set_tracing": (C.c_int, [_vp, C.c_int]),
     "vors_batch_last_trace": (C.c_int, [_vp, C.c_uint32, _P(TraceRec), C.c_int, _P(C.c_int)]),
     "vors_batch_destroy": (None, [_vp]),
@@ -151,6 +153,28 @@ def load_library() -> C.CDLL:
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+def source_hash() -> str:
+    """sha256/16 over the CUDA sources and headers, computed the way the Makefile does (SRC then HDR order)."""
+    import hashlib
+
+    pkg = os.path.dirname(_HERE)
+    files = ["csrc/image_kernels.cu", "csrc/dso_kernels.cu", "csrc/align_kernel.cu", "csrc/engine.cu",
+             "csrc/vors_device.cuh", "csrc/lie.cuh", "../include/vors_b200.h"]
+    h = hashlib.sha256()
+    for f in files:
+        with open(os.path.join(pkg, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def build_info() -> dict:
+    """What the loaded libvors_b200.so says it was built from, and whether that matches the sources in the tree."""
+    info = dict(kv.split("=", 1) for kv in load_library().vors_build_info().decode().split())
+    info["tree_src"] = source_hash()
+    info["matches_tree"] = info.get("src") == info["tree_src"]
+    return info
 
 
 def _check(rc: int, allow_failed: bool = False) -> int:
@@ -340,6 +364,12 @@ class BatchTracker:
     def last_counters(self):
         a, b = C.c_uint64(), C.c_uint64()
         _check(self._lib.vors_batch_last_counters(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def last_launch_shape(self):
+        """(CTAs per alignment, alignments in flight) of the last align launch."""
+        a, b = C.c_int(), C.c_int()
+        _check(self._lib.vors_batch_last_launch_shape(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
     def last_trace(self, stream, cap=256):

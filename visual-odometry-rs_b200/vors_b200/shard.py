@@ -48,3 +48,94 @@ def gather_poses(local_records, n_items: int, device=None):
         idx = partition(n_items, r, world)
         full[idx] = out[r][: len(idx)].cpu().numpy()
     return full
+
+
+class PoseGatherer:
+    """The per-step pose exchange without a host round trip on the critical path.
+
+    `gather_poses` above is the simple synchronous form (tests, one-off calls).  In a stepping loop it serialises a
+    H2D copy, the collective and `world` blocking device->host copies between two launches of the align kernel, with
+    nothing in flight on the GPU meanwhile.  This class keeps everything preallocated and asynchronous instead:
+
+      submit(records)  packs the step's records into a pinned host slot, copies them to a preallocated device buffer,
+                       issues ONE `all_gather_into_tensor` (NCCL; gloo falls back to the list form on CPU tensors) and
+                       ONE device->host copy of the gathered block into pinned memory, all on a side stream, and
+                       returns immediately - the caller launches its next step while the exchange is in flight;
+      collect()        waits for the oldest outstanding exchange and returns its records in GLOBAL item order.
+
+    `depth` slots are in flight at most (default 2: the gather of step k overlaps the kernels of step k+1).
+    Ranks own `partition(n_items, rank, world)`; shards are padded to the largest shard.
+    """
+
+    def __init__(self, n_items: int, device=None, depth: int = 2):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.n_items = int(n_items)
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.world = dist.get_world_size() if self.active else 1
+        self.rank = dist.get_rank() if self.active else 0
+        self.per = (self.n_items + self.world - 1) // self.world
+        self.n_local = len(partition(self.n_items, self.rank, self.world))
+        self.device = torch.device(device) if device is not None else torch.device("cpu")
+        self.cuda = self.device.type == "cuda"
+        self.depth = max(1, int(depth))
+        pin = self.cuda
+        self.h_in = [torch.zeros((self.per, POSE_RECORD_FLOATS), dtype=torch.float32, pin_memory=pin) for _ in range(self.depth)]
+        self.h_out = [torch.zeros((self.world * self.per, POSE_RECORD_FLOATS), dtype=torch.float32, pin_memory=pin)
+                      for _ in range(self.depth)]
+        if self.cuda:
+            self.d_in = [torch.zeros((self.per, POSE_RECORD_FLOATS), dtype=torch.float32, device=self.device) for _ in range(self.depth)]
+            self.d_out = [torch.zeros((self.world * self.per, POSE_RECORD_FLOATS), dtype=torch.float32, device=self.device)
+                          for _ in range(self.depth)]
+            self.stream = torch.cuda.Stream(device=self.device)
+            self.done = [torch.cuda.Event() for _ in range(self.depth)]
+        # global item index of row j of the gathered block: rank r's i-th record is item r + i * world
+        idx = np.full(self.world * self.per, -1, np.int64)
+        for r in range(self.world):
+            own = partition(self.n_items, r, self.world)
+            idx[r * self.per: r * self.per + len(own)] = own
+        self._rows = np.nonzero(idx >= 0)[0]
+        self._items = idx[self._rows]
+        self._head = 0          # next slot to submit into
+        self._pending = []      # slots in flight, oldest first
+        self.submitted = 0
+
+    def submit(self, poses: np.ndarray, status: np.ndarray) -> None:
+        """Start the exchange of this step's local records (poses [n_local, 7], status [n_local])."""
+        torch, dist = self.torch, self.dist
+        if len(self._pending) == self.depth:
+            raise RuntimeError("PoseGatherer: collect() the oldest exchange before submitting another")
+        s = self._head
+        self._head = (s + 1) % self.depth
+        h = self.h_in[s].numpy()
+        h[: self.n_local, :7] = poses
+        h[: self.n_local, 7] = status
+        if not self.active:
+            self.h_out[s][: self.per].copy_(self.h_in[s])
+        elif self.cuda:
+            with torch.cuda.stream(self.stream):
+                self.d_in[s].copy_(self.h_in[s], non_blocking=True)
+                dist.all_gather_into_tensor(self.d_out[s], self.d_in[s])
+                self.h_out[s].copy_(self.d_out[s], non_blocking=True)
+                self.done[s].record(self.stream)
+        else:  # gloo on CPU tensors (tests)
+            parts = list(self.h_out[s].view(self.world, self.per, POSE_RECORD_FLOATS).unbind(0))
+            dist.all_gather(parts, self.h_in[s])
+        self._pending.append(s)
+        self.submitted += 1
+
+    def collect(self) -> np.ndarray:
+        """Records of the oldest outstanding exchange in global item order: [n_items, 8] (a fresh array)."""
+        if not self._pending:
+            raise RuntimeError("PoseGatherer: nothing in flight")
+        s = self._pending.pop(0)
+        if self.active and self.cuda:
+            self.done[s].synchronize()
+        full = np.zeros((self.n_items, POSE_RECORD_FLOATS), np.float32)
+        full[self._items] = self.h_out[s].numpy()[self._rows]
+        return full
+
+    def in_flight(self) -> int:
+        return len(self._pending)
