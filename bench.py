@@ -139,7 +139,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_streams(cfg, n_streams, n_frames, seed0, device):
+def make_streams(cfg, n_streams, n_frames, seed0, device, **traj_kw):
     """Per stream: its own textured-plane scene and smooth trajectory.  Returns torch tensors
     gray u8 [n_frames, n_streams, rows, cols], depth u16 (same shape), gt poses [n_frames, n_streams, 7], scene0."""
     import torch
@@ -153,7 +153,7 @@ def make_streams(cfg, n_streams, n_frames, seed0, device):
     for s in range(n_streams):
         scene = synth.make_scene(seed0 + s, rows, cols)
         scene0 = scene0 or scene
-        poses = synth.trajectory(seed0 + s, n_frames)
+        poses = synth.trajectory(seed0 + s, n_frames, **traj_kw)
         g, d = synth.render_batch_torch(scene, poses, device, frame_seed=s, chunk=n_frames)
         gray[:, s] = g
         depth[:, s] = d.to(torch.uint16)
@@ -393,9 +393,18 @@ def oracle_cfg(kw):
 
 
 def parity_in_run(cfg, gray_h, depth_h, kw, n_streams, T, fi, poses_log):
-    """The oracle INSIDE the benchmarked path: the CPU oracle's parity build (-O2 -ffp-contract=off, the reference's
-    sequential f32 sums) tracks the very frames the two GPU arms were given, for the first `n_streams` streams and every
-    step of the run (warm-up + timed), one stream per host thread; pose differences are taken after every step."""
+    """The oracle INSIDE the benchmarked path: the CPU oracle's parity build (-O2 -ffp-contract=off) tracks the very frames
+    the two GPU arms were given, for the first `n_streams` streams and every step of the run (warm-up + timed), one stream
+    per host thread; pose differences are taken after every step.
+
+    Which oracle decides `ok`.  The reference sums r^2, J r and J J^T sequentially in f32 (lm_optimizer.rs:68-107), which is
+    exact enough for the candidate counts the reference itself produces (coarse-to-fine / DSO: a few thousand per level), so
+    for those configs the reference-faithful oracle decides.  DENSE candidates are an extension the reference never runs: a
+    sequential f32 sum over 3e5 terms carries ~4e-4 of relative round-off (tests/test_gpu_parity.py), more than the margins
+    of the LM accept / reject tests near convergence, so the faithful oracle's own decisions become coin flips and, with a
+    fixed number of rounds, move its pose by 1e-5..1e-4.  There the oracle with f64 accumulation decides (same algorithm,
+    sums as accurate as the GPU's), the faithful one is reported next to it, and so is the distance between the two oracles,
+    which is the yardstick for what the summation order alone does to a pose."""
     import concurrent.futures as cf
 
     from oracle import oracle_py as O
@@ -403,8 +412,12 @@ def parity_in_run(cfg, gray_h, depth_h, kw, n_streams, T, fi, poses_log):
     O.build()
     ocfg = oracle_cfg(kw)
     t0 = time.perf_counter()
+    dense = cfg["mode"] == DENSE
+    modes = ["f32_sequential", "f64"] if dense else ["f32_sequential"]
 
-    def one(s):
+    def one(job):
+        s, mode = job
+        O.lib().ref_set_accum_f64(1 if mode == "f64" else 0)  # thread-local switch of the oracle
         tr = O.Tracker(ocfg, 0.0, depth_h[0, s].numpy(), 0.0, gray_h[0, s].numpy(), fast=False)
         out = np.zeros((T + 1, 7), np.float32)
         sw = 0
@@ -412,29 +425,39 @@ def parity_in_run(cfg, gray_h, depth_h, kw, n_streams, T, fi, poses_log):
             _, st, _ = tr.track(float(k), depth_h[fi(k), s].numpy(), float(k), gray_h[fi(k), s].numpy())
             sw += st.keyframe_changed
             out[k] = tr.current_frame()[1].as_array()
+        O.lib().ref_set_accum_f64(0)
         return out, sw
 
-    with cf.ThreadPoolExecutor(max_workers=min(n_streams, os.cpu_count() or 1)) as pool:
-        res = list(pool.map(one, range(n_streams)))
-    oracle_poses = np.stack([r[0] for r in res], 1)  # [T+1, P, 7]
-    worst = {}
-    for arm, gp in poses_log.items():
+    jobs = [(s, m) for m in modes for s in range(n_streams)]
+    with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+        res = list(pool.map(one, jobs))
+    oracle_poses = {m: np.stack([res[i * n_streams + s][0] for s in range(n_streams)], 1) for i, m in enumerate(modes)}  # [T+1, P, 7]
+
+    def worst(a, b):
         mr = mm = 0.0
         for k in range(1, T + 1):
             for s in range(n_streams):
-                a, m = O.pose_error(gp[k, s], oracle_poses[k, s])
-                mr, mm = max(mr, a), max(mm, m)
-        worst[arm] = (mr, mm)
-    max_rad = max(v[0] for v in worst.values())
-    max_m = max(v[1] for v in worst.values())
-    return {"streams": n_streams, "frames": T, "alignments_compared": 2 * n_streams * T,
-            "max_rad": max_rad, "max_m": max_m, "tol_rad": PARITY_TOL_RAD, "tol_m": PARITY_TOL_M,
-            "ok": bool(max_rad <= PARITY_TOL_RAD and max_m <= PARITY_TOL_M),
-            "per_arm": {a: {"max_rad": v[0], "max_m": v[1]} for a, v in worst.items()},
-            "oracle_keyframe_switches": int(sum(r[1] for r in res)),
-            "oracle": "C++ restatement, parity build (-O2 -ffp-contract=off), the reference's sequential f32 accumulation; "
-                      "compared after every step of both arms (device-resident and host/announced)",
-            "seconds": time.perf_counter() - t0}
+                r, m = O.pose_error(a[k, s], b[k, s])
+                mr, mm = max(mr, r), max(mm, m)
+        return {"max_rad": mr, "max_m": mm}
+
+    against = {m: {arm: worst(gp, oracle_poses[m]) for arm, gp in poses_log.items()} for m in modes}
+    decides = "f64" if dense else "f32_sequential"
+    max_rad = max(v["max_rad"] for v in against[decides].values())
+    max_m = max(v["max_m"] for v in against[decides].values())
+    out = {"streams": n_streams, "frames": T, "alignments_compared": 2 * n_streams * T,
+           "max_rad": max_rad, "max_m": max_m, "tol_rad": PARITY_TOL_RAD, "tol_m": PARITY_TOL_M,
+           "ok": bool(max_rad <= PARITY_TOL_RAD and max_m <= PARITY_TOL_M),
+           "deciding_oracle": decides, "per_oracle_per_arm": against,
+           "oracle_keyframe_switches": int(sum(r[1] for r in res[:n_streams])),
+           "oracle": "C++ restatement, parity build (-O2 -ffp-contract=off); f32_sequential = the reference's own accumulation "
+                     "(decides for the reference's candidate modes), f64 = same algorithm with f64 sums (decides for the dense "
+                     "extension); compared after every step of both arms (device-resident and host/announced)",
+           "seconds": 0.0}
+    if dense:
+        out["oracle_f32_vs_f64"] = worst(oracle_poses["f32_sequential"], oracle_poses["f64"])
+    out["seconds"] = time.perf_counter() - t0
+    return out
 
 
 def cpu_baseline_port(gray_h, depth_h, kw, n_streams, n_frames):

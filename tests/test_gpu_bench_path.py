@@ -4,7 +4,13 @@ walked back and forth with keyframe switches, through BOTH entry points the benc
 step ahead, and pinned host frames announced one step ahead), against one oracle Tracker per stream.
 
 296 streams are 8 distinct scenes replicated 37 times: the oracle only has to track 8 streams, and the replicas double as a
-determinism check (identical inputs must give bit-identical poses whatever CTA / SM they ran on)."""
+determinism check (identical inputs must give bit-identical poses whatever CTA / SM they ran on).
+
+Dense candidates are an extension: over 3e5 terms the reference's sequential f32 sums carry ~4e-4 of relative round-off, more
+than the margins of the LM accept / reject tests near convergence, so the reference-faithful oracle's own decisions flip against
+its f64-accumulating twin (1-11 of 55 per alignment, poses apart by up to ~4e-5 m: `oracle_f32_vs_f64` below).  The GPU (f32
+partials, f64 totals) is therefore graded against the f64-accumulating oracle - pose <= 1e-4 and decision traces - and its
+distance to the faithful oracle is reported next to the oracles' own spread."""
 import concurrent.futures as cf
 import ctypes as C
 import os
@@ -28,12 +34,13 @@ def test_benchmarked_path_team1_dense_296_streams(oracle, record_property):
 
     import bench
     import vors_b200 as vb
-    from test_gpu_parity import DENSE_E_TOL, _same_trace
+    from test_gpu_parity import _same_trace
 
     assert vb.device_count() > 0
     device = torch.device("cuda", 0)
     cfg = bench.CONFIGS[2]
-    gray, depth, _, scene = bench.make_streams(cfg, N_DISTINCT, N_RENDER, 424200, device)  # [F+1, 8, rows, cols]
+    # twice the bench's camera speed: every stream crosses the 1 px keyframe threshold during the walk
+    gray, depth, _, scene = bench.make_streams(cfg, N_DISTINCT, N_RENDER, 424200, device, step_v=0.008, step_w=0.006)  # [F+1, 8, rows, cols]
     F = N_RENDER - 1
     rep = torch.arange(N_STREAMS, device=device) % N_DISTINCT
     gray_h = gray.cpu()
@@ -46,8 +53,10 @@ def test_benchmarked_path_team1_dense_296_streams(oracle, record_property):
     status = np.zeros(N_STREAMS, np.int32)
     stats = (vb.TrackStats * N_STREAMS)()
 
-    # ---- oracle: one Tracker per distinct stream, parity build, reference-faithful sequential f32 sums
-    def run_oracle(s):
+    # ---- oracles: one Tracker per distinct stream, parity build; f64 sums (grades the GPU) and the faithful sequential f32
+    def run_oracle(job):
+        s, f64 = job
+        oracle.lib().ref_set_accum_f64(f64)  # thread-local
         tr = oracle.Tracker(ocfg, 0.0, depth_h[0, s].numpy(), 0.0, gray_h[0, s].numpy())
         poses, traces, switches = [], [], 0
         for k in range(1, N_STEPS + 1):
@@ -56,11 +65,17 @@ def test_benchmarked_path_team1_dense_296_streams(oracle, record_property):
             poses.append(tr.current_frame()[1].as_array())
             traces.append(trace)
             switches += st.keyframe_changed
+        oracle.lib().ref_set_accum_f64(0)
         return poses, traces, switches
 
-    with cf.ThreadPoolExecutor(max_workers=min(N_DISTINCT, os.cpu_count() or 1)) as pool:
-        ref = list(pool.map(run_oracle, range(N_DISTINCT)))
-    assert sum(r[2] for r in ref) >= 1, "the walk must include keyframe switches"
+    with cf.ThreadPoolExecutor(max_workers=min(2 * N_DISTINCT, os.cpu_count() or 1)) as pool:
+        both = list(pool.map(run_oracle, [(s, a) for a in (1, 0) for s in range(N_DISTINCT)]))
+    ref, ref32 = both[:N_DISTINCT], both[N_DISTINCT:]
+    spread = (0.0, 0.0)
+    for s in range(N_DISTINCT):
+        for a, b in zip(ref[s][0], ref32[s][0]):
+            e = oracle.pose_error(a, b)
+            spread = (max(spread[0], e[0]), max(spread[1], e[1]))
 
     def new_tracker():
         g0 = gray_h[0].numpy()[rep.cpu().numpy()]
@@ -73,21 +88,23 @@ def test_benchmarked_path_team1_dense_296_streams(oracle, record_property):
         assert bt.last_launch_shape()[0] == 1, "the benchmarked configuration is one alignment per CTA (team == 1)"
         assert not status.any()
         _, poses = bt.current_frames()
-        worst = (0.0, 0.0)
+        worst = (0.0, 0.0, 0.0, 0.0)
         for s in range(N_DISTINCT):
             assert np.array_equal(poses[s::N_DISTINCT], np.broadcast_to(poses[s], poses[s::N_DISTINCT].shape)), \
                 f"replicas of stream {s} differ at step {k}: the reduction is not order-deterministic"
             ang, dist = oracle.pose_error(poses[s], ref[s][0][k - 1])
             assert ang <= 1e-4 and dist <= 1e-4, (k, s, ang, dist)
-            worst = (max(worst[0], ang), max(worst[1], dist))
+            a32, d32 = oracle.pose_error(poses[s], ref32[s][0][k - 1])
+            worst = (max(worst[0], ang), max(worst[1], dist), max(worst[2], a32), max(worst[3], d32))
             assert stats[s].n_passes == 55 and list(stats[s].n_iters)[:5] == [10] * 5
-            ties.append(_same_trace(bt.last_trace(s, 512), ref[s][1][k - 1], DENSE_E_TOL))
+            # against f64 sums the energies agree to the GPU's own round-off: the tight (non-dense) tolerances apply
+            ties.append(_same_trace(bt.last_trace(s, 512), ref[s][1][k - 1], max_ties=5))
         return worst
 
     results = {}
     # ---- (a) device-resident frames, next step announced (bench.py `value`)
     bt = new_tracker()
-    ties, worst = [], (0.0, 0.0)
+    ties, worst = [], (0.0,) * 4
     depth_i16 = depth.view(torch.int16)  # same bits; index_select has no uint16 kernel
     cm = lambda t, f: t[f].index_select(0, rep).transpose(-1, -2).contiguous()  # [296, cols, rows] = column-major frames
     nxt_g = cm(gray, _walk(1, F))
@@ -95,11 +112,13 @@ def test_benchmarked_path_team1_dense_296_streams(oracle, record_property):
         f = _walk(k, F)
         g, d = nxt_g, cm(depth_i16, f)
         nxt_g = cm(gray, _walk(k + 1, F)) if k < N_STEPS else None
+        torch.cuda.synchronize()  # the library's streams are not ordered after torch's: the buffers must be complete
         bt.track_device(ts[k].ctypes.data, d.data_ptr(), ts[k].ctypes.data, g.data_ptr(), status.ctypes.data, C.addressof(stats),
                         nxt_g.data_ptr() if nxt_g is not None else None)
         w = check_step(bt, k, ties)
-        worst = (max(worst[0], w[0]), max(worst[1], w[1]))
-    results["device"] = dict(max_rad=worst[0], max_m=worst[1], ties=int(sum(ties)), traces=len(ties))
+        worst = tuple(max(a, b) for a, b in zip(worst, w))
+    results["device"] = dict(max_rad=worst[0], max_m=worst[1], vs_f32_oracle_rad=worst[2], vs_f32_oracle_m=worst[3],
+                             ties=int(sum(ties)), traces=len(ties))
     del bt
 
     # ---- (b) pinned host frames, next step announced (bench.py `e2e`)
@@ -109,18 +128,23 @@ def test_benchmarked_path_team1_dense_296_streams(oracle, record_property):
     iptr = [(C.c_void_p * N_STREAMS)(*[gray_p[f].data_ptr() + int(r) * I for r in repl]) for f in range(F + 1)]
     dptr = [(C.c_void_p * N_STREAMS)(*[depth_p[f].data_ptr() + int(r) * I * 2 for r in repl]) for f in range(F + 1)]
     bt = new_tracker()
-    ties, worst = [], (0.0, 0.0)
+    ties, worst = [], (0.0,) * 4
     for k in range(1, N_STEPS + 1):
         f = _walk(k, F)
         bt.track_raw(ts[k].ctypes.data, dptr[f], ts[k].ctypes.data, iptr[f], status.ctypes.data, C.addressof(stats),
                      iptr[_walk(k + 1, F)] if k < N_STEPS else None)
         w = check_step(bt, k, ties)
-        worst = (max(worst[0], w[0]), max(worst[1], w[1]))
-    results["host_announced"] = dict(max_rad=worst[0], max_m=worst[1], ties=int(sum(ties)), traces=len(ties))
+        worst = tuple(max(a, b) for a, b in zip(worst, w))
+    results["host_announced"] = dict(max_rad=worst[0], max_m=worst[1], vs_f32_oracle_rad=worst[2], vs_f32_oracle_m=worst[3],
+                                     ties=int(sum(ties)), traces=len(ties))
     del bt
 
+    results["oracle_f32_vs_f64"] = dict(max_rad=spread[0], max_m=spread[1])
+    results["oracle_keyframe_switches"] = int(sum(r[2] for r in ref))
+    assert results["oracle_keyframe_switches"] >= 1, "the walk must include keyframe switches"
     record_property("benchmarked_path_parity", results)
     print("benchmarked path vs oracle:", results)
     # the number of near-tie divergences the trace comparator tolerated, reported rather than hidden
-    for arm, r in results.items():
+    for arm in ("device", "host_announced"):
+        r = results[arm]
         assert r["ties"] <= r["traces"] // 10, f"{arm}: {r['ties']} near-tie divergences in {r['traces']} traces"
