@@ -21,7 +21,7 @@
     } while (0)
 
 constexpr int kRows = 480, kCols = 640, kImages = 296, kWarps = 10, kFiller = 40;
-constexpr int kPerRow = 128;                       // images side by side along texture x
+constexpr int kPerRow = 64;                        // images side by side along texture x (2D gather textures: <= 32768 x 32768)
 constexpr int kCellW = kRows + 2, kCellH = kCols + 2;  // + two never-written (zero) texels: the zero page
 
 struct Params {
@@ -107,6 +107,10 @@ __global__ void k_fill(const uint8_t* __restrict__ linear, cudaSurfaceObject_t s
     }
 }
 
+__global__ void k_to_half(const uint8_t* __restrict__ in, __half* __restrict__ out, size_t n) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) out[i] = __float2half_rn(float(in[i]));
+}
+
 int main() {
     const size_t I = size_t(kRows) * kCols;
     std::vector<uint8_t> host(I * kImages);
@@ -133,7 +137,15 @@ int main() {
         float fill_ms = 0.0f;
         if (variant) {
             const cudaChannelFormatDesc fmt = variant == 1 ? cudaCreateChannelDesc<uint8_t>() : cudaCreateChannelDescHalf();
-            CK(cudaMallocArray(&arr, &fmt, W, H, cudaArrayTextureGather | cudaArraySurfaceLoadStore));
+            bool surface_ok = true;
+            if (cudaMallocArray(&arr, &fmt, W, H, cudaArrayTextureGather | cudaArraySurfaceLoadStore) != cudaSuccess) {
+                (void)cudaGetLastError();
+                surface_ok = false;
+                printf("   gather + surface flags together: rejected for %d x %d; gather-only array, filled by cudaMemcpy2DToArray\n", W, H);
+                CK(cudaMallocArray(&arr, &fmt, W, H, cudaArrayTextureGather));
+            } else {
+                printf("   gather + surface flags together: accepted for %d x %d\n", W, H);
+            }
             // zero the whole array (gaps = zero page) with a copy from a zeroed linear buffer
             void* z;
             const size_t pitch = size_t(W) * (variant == 1 ? 1 : 2);
@@ -144,7 +156,7 @@ int main() {
             cudaResourceDesc res{};
             res.resType = cudaResourceTypeArray;
             res.res.array.array = arr;
-            CK(cudaCreateSurfaceObject(&surf, &res));
+            if (surface_ok) CK(cudaCreateSurfaceObject(&surf, &res));
             cudaTextureDesc td{};
             td.addressMode[0] = td.addressMode[1] = cudaAddressModeBorder;
             td.filterMode = cudaFilterModePoint;
@@ -153,8 +165,21 @@ int main() {
             CK(cudaCreateTextureObject(&p.tex, &res, &td, nullptr));
             for (int rep = 0; rep < 2; ++rep) {
                 CK(cudaEventRecord(e0));
-                if (variant == 1) k_fill<false><<<dim3(64, kImages), 256>>>(d_linear, surf);
-                else k_fill<true><<<dim3(64, kImages), 256>>>(d_linear, surf);
+                if (surface_ok) {
+                    if (variant == 1) k_fill<false><<<dim3(64, kImages), 256>>>(d_linear, surf);
+                    else k_fill<true><<<dim3(64, kImages), 256>>>(d_linear, surf);
+                } else {
+                    // one 2D copy per image (column-major image = kCols rows of kRows texels); f16: converted into a linear staging buffer first
+                    static __half* stage = nullptr;
+                    if (variant == 2 && !stage) CK(cudaMalloc(&stage, I * kImages * sizeof(__half)));
+                    if (variant == 2) k_to_half<<<1024, 256>>>(d_linear, stage, I * kImages);
+                    for (int i = 0; i < kImages; ++i) {
+                        const size_t esz = variant == 1 ? 1 : 2;
+                        const void* src = variant == 1 ? (const void*)(d_linear + size_t(i) * I) : (const void*)(stage + size_t(i) * I);
+                        CK(cudaMemcpy2DToArrayAsync(arr, size_t((i % kPerRow) * kCellW) * esz, size_t((i / kPerRow) * kCellH), src, kRows * esz, kRows * esz, kCols,
+                                                    cudaMemcpyDeviceToDevice, 0));
+                    }
+                }
                 CK(cudaEventRecord(e1));
                 CK(cudaEventSynchronize(e1));
             }
@@ -187,7 +212,7 @@ int main() {
             }
             printf("   vs ldg4: max relative difference of the per-image sums %.3e, %d of %d sums bit-identical\n", worst, exact, kImages);
             CK(cudaDestroyTextureObject(p.tex));
-            CK(cudaDestroySurfaceObject(surf));
+            if (surf) CK(cudaDestroySurfaceObject(surf));
             CK(cudaFreeArray(arr));
         }
     }
