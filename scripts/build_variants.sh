@@ -12,7 +12,7 @@ for spec in "$@"; do
   name="${spec%%:*}"; defs="${spec#*:}"
   $NVCC $FLAGS $defs -c csrc/align_kernel.cu -o build/variants/$name.o 2> build/variants/$name.log
   OTHERS="build/image_kernels.o build/dso_kernels.o build/engine.o"
-  if [[ "$defs" == *VORS_STAGE_CHUNKS* ]]; then  # the record padding is shared with the keyframe kernels and the engine
+  if [[ "$defs" == *VORS_STAGE_CHUNKS* || "$defs" == *VORS_TEX* ]]; then  # shared with the keyframe kernels and the engine
     OTHERS=""
     for f in image_kernels dso_kernels engine; do
       $NVCC $FLAGS $defs -c csrc/$f.cu -o build/variants/${name}_$f.o 2> /dev/null
@@ -20,5 +20,5 @@ for spec in "$@"; do
     done
   fi
   $NVCC -shared $ARCH -o lib_variants/$name.so $OTHERS build/variants/$name.o
-  echo "$name: $(grep -A2 'k_alignILb0' build/variants/$name.log | grep -E 'registers|spill' | tr '\n' ' ' | sed -E 's/ptxas info    ://g')"
+  echo "$name: $(grep -A2 'k_alignILb0ELb0ELb1' build/variants/$name.log | grep -E 'registers|spill' | tr '\n' ' ' | sed -E 's/ptxas info    ://g')"
 done

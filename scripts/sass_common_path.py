@@ -17,19 +17,21 @@ CUBIN = "/tmp/vors_align.cubin"
 
 
 def main():
-    flags = sys.argv[1:]
+    flags = [a for a in sys.argv[1:] if a != "--tiled"]
+    # which instantiation: the sparse-record kernel k_align<false, false, false> or (--tiled) the tiled dense one <false, false, true>
+    KEY = "k_alignILb0ELb0ELb1E" if "--tiled" in sys.argv else "k_alignILb0ELb0ELb0E"
     cmd = ["/usr/local/cuda/bin/nvcc", "-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
            "--expt-relaxed-constexpr", "-Xptxas", "-v", *flags, "-cubin", SRC, "-o", CUBIN]
     log = subprocess.run(cmd, capture_output=True, text=True, check=True).stderr
     lines = log.splitlines()
     for i, l in enumerate(lines):
-        if "k_alignILb0ELb0E" in l:
+        if KEY in l:
             print(" | ".join(x.replace("ptxas info    :", "").strip() for x in lines[i + 1:i + 3]))
     sass = subprocess.run(["cuobjdump", "-sass", CUBIN], capture_output=True, text=True, check=True).stdout
     ins, on = [], False
     for l in sass.splitlines():
         if "Function :" in l:
-            on = "k_alignILb0ELb0E" in l
+            on = KEY in l
         m = re.match(r"\s+/\*([0-9a-f]{4,5})\*/\s+(.*?);", l)
         if on and m:
             ins.append((int(m.group(1), 16), m.group(2).strip()))

@@ -54,6 +54,9 @@ namespace {
 #ifndef VORS_STAGES
 #define VORS_STAGES 2
 #endif
+#ifndef VORS_FRND
+#define VORS_FRND 0     // 1: floor by FRND.FLOOR (one XU-pipe instruction) instead of the round-down magic-number add + subtract
+#endif
 constexpr int kWarps = VORS_WARPS;            // warps per CTA; every warp refills its own TMA ring
 constexpr int kConsumers = kWarps * 32;
 constexpr int kBlock = kConsumers;
@@ -247,6 +250,10 @@ struct LevelConst {
     float wm2, hm2;
     float zero_u, zero_v;
     float magic_u, magic_v;     // floor constants Cu, Cv (see kMagicBits)
+    float tex_ku, tex_kv;       // texture path: (2^23 + floor) - tex_k = atlas coordinate of the footprint's shared corner
+    unsigned long long tex;     // atlas page of this job's frame
+    int tiles_y;                // tiled records: tiles per tile column
+    float inv_tiles_y;
     uint32_t rows;
     int n;
     const uint8_t* img_biased;  // img - ((bits(Cu) * rows + bits(Cv)) mod 2^32)
@@ -279,8 +286,25 @@ __device__ __forceinline__ void choose_floor_magic(LevelConst& c, const uint8_t*
 struct Front {
     uint32_t pk, gr;
     float a, b, rho, fa, fb;
+#if VORS_TEX
+    float t00, t10, t01, t11;  // texels as the texture unit returns them (texel / 255, or the exact value with f16 texels)
+#else
     uint32_t t00, t10, t01, t11;
+#endif
 };
+#if VORS_TEX
+#if VORS_TEX_F16
+constexpr float kTexScale = 1.0f;
+#else
+constexpr float kTexScale = 255.0f;
+#endif
+// One texture gather = the 2x2 footprint.  (tx, ty) is the corner shared by the four texels (integer-valued, half a texel
+// away from every footprint boundary: the texture unit's fixed-point coordinates cannot select another footprint than the
+// kernel's own floor).  Texture x = image y: .w = (y, x), .z = (y+1, x), .x = (y, x+1), .y = (y+1, x+1).
+__device__ __forceinline__ void tex_gather(unsigned long long tex, float tx, float ty, float& t00, float& t10, float& t01, float& t11) {
+    asm("tld4.r.2d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6}];" : "=f"(t01), "=f"(t11), "=f"(t10), "=f"(t00) : "l"(tex), "f"(tx), "f"(ty));
+}
+#endif
 
 // The kernel's shared state: the LM / ring block in dynamic shared memory, the per-level constants in static.
 extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -296,17 +320,44 @@ __shared__ LevelConst s_lc;
 // J J^T to H_outside.  Keeping all of this (and its function calls) out of the hot loop keeps that loop call-free.
 constexpr int kNearWords = 32;  // flagged bitmap words a warp remembers per pass (beyond that: full bitmap scan)
 
+// Fields of candidate slot `i` of a level, from its record in global memory (deferred pass, optical flow).
+struct SlotRec {
+    float x, y, rho, gu, gv, tmpl;
+};
+template <bool kTiled>
+__device__ __forceinline__ SlotRec load_slot(const uint32_t* __restrict__ pts, int tiles_y, int i) {
+    SlotRec r;
+    if constexpr (kTiled) {
+        const int st = i / kTileSlots, j = (i / kTileRows) % kTileCols, ln = i % kTileRows;
+        const int tx = st / tiles_y, ty = st - tx * tiles_y;
+        const uint32_t* w = pts + size_t(st) * kTileWords;
+        r.x = float(kTileCols * tx + j);
+        r.y = float(kTileRows * ty + ln);
+        r.rho = __uint_as_float(__ldg(w + tile_rho_word(j, ln)));
+        const uint32_t gr = __ldg(w + tile_grad_word(j, ln));
+        r.gu = rec_gx(gr);
+        r.gv = rec_gy(gr);
+        r.tmpl = __half2float(__ushort_as_half(__ldg(reinterpret_cast<const unsigned short*>(w) + tile_tmpl_half(j, ln))));
+    } else {
+        const uint32_t pk = __ldg(pts + pt_word(i, 0)), gr = __ldg(pts + pt_word(i, 2));
+        r.rho = __uint_as_float(__ldg(pts + pt_word(i, 1)));
+        r.x = float(rec_x(pk));
+        r.y = float(rec_y(pk));
+        r.gu = rec_gx(gr);
+        r.gv = rec_gy(gr);
+        r.tmpl = float(rec_tmpl(pk));
+    }
+    return r;
+}
+
 // One deferred candidate: the reference's own warp decides (lm_optimizer.rs:213-231); inside -> full evaluation into
 // `acc`, outside -> J J^T into h.
-template <bool kSkew, bool kHuber>
+template <bool kSkew, bool kHuber, bool kTiled>
 __device__ __forceinline__ void eval_deferred(int i, const LevelConst& lc, const Pose& model, Acc<kHuber>& acc, int& fixed, float (&h)[21]) {
-    const uint32_t* __restrict__ pts = lc.pts;
     const Intrinsics k = lc.k;
     const int rows = int(lc.rows);
-    const uint32_t pk = __ldg(pts + pt_word(i, 0)), gr = __ldg(pts + pt_word(i, 2));
-    const float rho = __uint_as_float(__ldg(pts + pt_word(i, 1)));
-    const float x = float(rec_x(pk)), y = float(rec_y(pk));
-    const float gu = rec_gx(gr), gv = rec_gy(gr);
+    const SlotRec sr = load_slot<kTiled>(lc.pts, lc.tiles_y, i);
+    const float rho = sr.rho, x = sr.x, y = sr.y, gu = sr.gu, gv = sr.gv;
     const float2 uv = warp_exact(model, k, x, y, rho);
     // 0 <= floor(u) < W-2  <=>  0 <= u < W-2 (W-2 is an integer); NaN compares false -> outside
     const bool inside = (uv.x >= 0.0f) && (uv.x < lc.wm2) && (uv.y >= 0.0f) && (uv.y < lc.hm2);
@@ -318,7 +369,7 @@ __device__ __forceinline__ void eval_deferred(int i, const LevelConst& lc, const
         const float t00 = float(__ldg(p)), t10 = float(__ldg(p + 1)), t01 = float(__ldg(p + rows)), t11 = float(__ldg(p + rows + 1));
         const float top = fmaf(a, t01 - t00, t00), bot = fmaf(a, t11 - t10, t10);
         const float val = fmaf(b, bot - top, top);  // same lerp form as `back`
-        const float r = val - float(rec_tmpl(pk));
+        const float r = val - sr.tmpl;
         ++fixed;
         if constexpr (kHuber) {
             float J[6];
@@ -347,7 +398,7 @@ __device__ __forceinline__ void eval_deferred(int i, const LevelConst& lc, const
 
 // `wlist`: the (word, mask) pairs this warp flagged in the hot loop (n_words of them, only the first kNearWords stored);
 // `scratch`: this warp's ring memory (idle between passes), used as the compacted candidate list.
-template <bool kSkew, bool kHuber>
+template <bool kSkew, bool kHuber, bool kTiled>
 __device__ __noinline__ void deferred_pass(int warp, int lane, int first_stage, int stage_stride, int n_stages, uint32_t* __restrict__ bitmap,
                                            const uint32_t* wlist, int n_words, uint32_t* scratch, Acc<kHuber>* acc_io, int* n_fix) {
     LmShared& S = lm_shared();
@@ -360,7 +411,7 @@ __device__ __noinline__ void deferred_pass(int warp, int lane, int first_stage, 
     // One round: every lane brings one flagged bitmap word (`mask` over the 32 slots starting at slot `base`); the set bits of
     // the whole warp are compacted into `scratch` (at most 1024 entries) and evaluated one candidate per lane and step.
     auto round = [&](uint32_t mask, int base) {
-        if (base + 32 > lc.n) mask = base >= lc.n ? 0u : (mask & ((1u << (lc.n - base)) - 1u));  // padding slots
+        if (!kTiled && base + 32 > lc.n) mask = base >= lc.n ? 0u : (mask & ((1u << (lc.n - base)) - 1u));  // padding slots
         const int cnt = __popc(mask);
         int incl = cnt;
 #pragma unroll
@@ -375,7 +426,7 @@ __device__ __noinline__ void deferred_pass(int warp, int lane, int first_stage, 
             mask &= mask - 1u;
         }
         __syncwarp();
-        for (int e = lane; e < total; e += 32) eval_deferred<kSkew, kHuber>(int(scratch[e]), lc, S.cand_model, acc, fixed, h);
+        for (int e = lane; e < total; e += 32) eval_deferred<kSkew, kHuber, kTiled>(int(scratch[e]), lc, S.cand_model, acc, fixed, h);
         __syncwarp();
     };
     if (n_words <= kNearWords) {
@@ -430,7 +481,55 @@ struct PassConst {
     float cx, cy, hu, hv, lo_u, lo_v, magic_u, magic_v, zero_u, zero_v;
     uint32_t rows;
     const uint8_t* img_biased;
+    float tex_ku, tex_kv;
+    unsigned long long tex;
 };
+
+// floor / fraction of a warped coordinate and the texel fetch of its 2x2 footprint (common tail of every front).
+__device__ __forceinline__ void sample_front(float u, float v, const PassConst& lc, Front& f) {
+#if VORS_TEX
+#if VORS_FRND
+    const float fu = floorf(u), fv = floorf(v);
+    f.fa = u - fu;
+    f.fb = v - fv;
+    tex_gather(lc.tex, fv + (8388608.0f - lc.tex_kv), fu + (8388608.0f - lc.tex_ku), f.t00, f.t10, f.t01, f.t11);
+#else
+    // tu = 2^23 + floor(u) exactly (round-down add; 0 <= u < 2^22 on this path)
+    const float tu = __fadd_rd(u, 8388608.0f), tv = __fadd_rd(v, 8388608.0f);
+    f.fa = u - (tu - 8388608.0f);
+    f.fb = v - (tv - 8388608.0f);
+    tex_gather(lc.tex, tv - lc.tex_kv, tu - lc.tex_ku, f.t00, f.t10, f.t01, f.t11);
+#endif
+#else
+    // floor and fraction without F2I / I2F (see kMagicBits)
+    const float tu = __fadd_rd(u, lc.magic_u), tv = __fadd_rd(v, lc.magic_v);
+    f.fa = u - (tu - lc.magic_u);
+    f.fb = v - (tv - lc.magic_v);
+    const uint8_t* p = lc.img_biased + (__float_as_uint(tu) * lc.rows + __float_as_uint(tv));
+    f.t00 = __ldg(p);
+    f.t10 = __ldg(p + 1);
+    f.t01 = __ldg(p + lc.rows);
+    f.t11 = __ldg(p + lc.rows + 1);
+#endif
+}
+
+// bilinear sample in lerp form minus the template value: the same interpolant as lm_optimizer.rs:241-246 (a along x, b along
+// y) with 6 instead of 10 operations; it differs from the reference's four-product expression by ~1 ulp of the value, far
+// inside the 1e-5 bar on the pass energy (tests/test_gpu_parity.py).  With normalised u8 texels the sample comes back in
+// units of 255 grey levels and is rescaled by the one FFMA that subtracts the template.
+__device__ __forceinline__ float residual_of(const Front& f, float tmpl) {
+    const float a = f.fa, b = f.fb;
+#if VORS_TEX
+    const float top = fmaf(a, f.t01 - f.t00, f.t00), bot = fmaf(a, f.t11 - f.t10, f.t10);
+    const float val = fmaf(b, bot - top, top);
+    return kTexScale == 1.0f ? val - tmpl : fmaf(kTexScale, val, -tmpl);
+#else
+    const float t00 = u2f(f.t00), t10 = u2f(f.t10);
+    const float top = fmaf(a, u2f(f.t01) - t00, t00), bot = fmaf(a, u2f(f.t11) - t10, t10);
+    const float val = fmaf(b, bot - top, top);
+    return val - tmpl;
+#endif
+}
 
 // Warp-uniform bookkeeping of the slots of a pass that the hot loop did not evaluate.
 struct Defer {
@@ -500,6 +599,39 @@ __device__ __forceinline__ FrontA front_a(uint32_t pk, float rho, uint32_t gr, c
     return o;
 }
 
+// The rare, warp-uniform part of a front: bookkeeping of the slots of this 32-slot word that the common path cannot evaluate.
+// `not_ok`: ballot of the lanes not inside for sure; `old_far`: the word's far-bitmap word from the previous pass of the level.
+template <bool kSkew, bool kHuber>
+__device__ __forceinline__ void rare_slots(unsigned not_ok, float u, float v, float rho, uint32_t gr, float a, float b, int word,
+                                           unsigned old_far, const PassConst& lc, const Intrinsics& k, Defer& df, float* hs, int lane) {
+    // H over the inside set = H_total - H_outside (lm_optimizer.rs:100 sums J J^T over the inside set).  H_outside is
+    // maintained incrementally across the passes of a level: only candidates that were outside for sure in the previous
+    // pass and are not now, or the reverse, add -+J J^T (after the first passes the pose barely moves: few flips).
+    const bool far = (fabsf(u - lc.hu) > s_lc.hi_u) | (fabsf(v - lc.hv) > s_lc.hi_v);  // outside for sure (false for NaN)
+    // padding slots and pixels without depth carry a NaN inverse depth: never `far`, and they need no second look
+    const unsigned live_mask = __ballot_sync(0xffffffffu, rho == rho);
+    const unsigned far_mask = __ballot_sync(0xffffffffu, far), near_mask = not_ok & ~far_mask & live_mask;
+    const unsigned flips = kHuber ? 0u : far_mask ^ old_far;  // (Huber weights: H is summed directly, nothing to maintain)
+    if (flips) {
+        const float sign = ((flips >> lane) & 1u) ? (far ? 1.0f : -1.0f) : 0.0f;
+        add_outside<kSkew>(sign, gr, a, b, rho, k, hs);
+        df.any_flip = 1;
+    }
+    if (lane == 0) {
+        if (flips) df.far[word] = far_mask;
+        if (near_mask) {  // boundary band / NaN coordinates of a live candidate: see deferred_pass
+            df.near[word] = near_mask;
+            if (df.n_words < kNearWords) {
+                df.wlist[2 * df.n_words] = uint32_t(word);
+                df.wlist[2 * df.n_words + 1] = near_mask;
+            }
+        }
+    }
+    df.n_words += near_mask ? 1 : 0;
+    df.n_bad += __popc(not_ok);
+    df.n_near += __popc(near_mask);
+}
+
 // front, second half: the rare paths (warp-uniform branch), floor / fraction, texel gathers.
 // `word` is the bitmap word of this call's 32 slots.
 // `old_words`: lane j holds the far-bitmap word of the stage's word j from the previous pass of the level; bit j of
@@ -513,33 +645,7 @@ __device__ __forceinline__ void front_b(const FrontA& x, int word, int j, unsign
     const unsigned not_ok = __ballot_sync(0xffffffffu, !ok);
     if (not_ok | (old_nz & (1u << j))) {  // warp-uniform, rare
         const unsigned old_far = __shfl_sync(0xffffffffu, old_words, j);
-        // H over the inside set = H_total - H_outside (lm_optimizer.rs:100 sums J J^T over the inside set).  H_outside is
-        // maintained incrementally across the passes of a level: only candidates that were outside for sure in the previous
-        // pass and are not now, or the reverse, add -+J J^T (after the first passes the pose barely moves: few flips).
-        const bool far = (fabsf(u - lc.hu) > s_lc.hi_u) | (fabsf(v - lc.hv) > s_lc.hi_v);  // outside for sure (false for NaN)
-        // padding slots (NaN inverse depth: never `far`) need no second look
-        const int n_live = s_lc.n - 32 * word;
-        const unsigned live_mask = n_live >= 32 ? 0xffffffffu : n_live <= 0 ? 0u : (1u << n_live) - 1u;
-        const unsigned far_mask = __ballot_sync(0xffffffffu, far), near_mask = not_ok & ~far_mask & live_mask;
-        const unsigned flips = kHuber ? 0u : far_mask ^ old_far;  // (Huber weights: H is summed directly, nothing to maintain)
-        if (flips) {
-            const float sign = ((flips >> lane) & 1u) ? (far ? 1.0f : -1.0f) : 0.0f;
-            add_outside<kSkew>(sign, x.gr, x.a, x.b, rho, k, hs);
-            df.any_flip = 1;
-        }
-        if (lane == 0) {
-            if (flips) df.far[word] = far_mask;
-            if (near_mask) {  // band / NaN / padding: see deferred_pass
-                df.near[word] = near_mask;
-                if (df.n_words < kNearWords) {
-                    df.wlist[2 * df.n_words] = uint32_t(word);
-                    df.wlist[2 * df.n_words + 1] = near_mask;
-                }
-            }
-        }
-        df.n_words += near_mask ? 1 : 0;
-        df.n_bad += __popc(not_ok);
-        df.n_near += __popc(near_mask);
+        rare_slots<kSkew, kHuber>(not_ok, u, v, rho, gr, x.a, x.b, word, old_far, lc, k, df, hs, lane);
         if (!ok) {
             u = lc.zero_u;
             v = lc.zero_v;
@@ -548,15 +654,7 @@ __device__ __forceinline__ void front_b(const FrontA& x, int word, int j, unsign
             gr = 0u;   // zero gradient: J = 0 (only the Huber path forms J on the common path)
         }
     }
-    // floor and fraction without F2I / I2F (see kMagicBits)
-    const float tu = __fadd_rd(u, lc.magic_u), tv = __fadd_rd(v, lc.magic_v);
-    f.fa = u - (tu - lc.magic_u);
-    f.fb = v - (tv - lc.magic_v);
-    const uint8_t* p = lc.img_biased + (__float_as_uint(tu) * lc.rows + __float_as_uint(tv));
-    f.t00 = __ldg(p);
-    f.t10 = __ldg(p + 1);
-    f.t01 = __ldg(p + lc.rows);
-    f.t11 = __ldg(p + lc.rows + 1);
+    sample_front(u, v, lc, f);
     f.pk = pk;
     f.gr = gr;
     f.a = x.a;
@@ -564,18 +662,62 @@ __device__ __forceinline__ void front_b(const FrontA& x, int word, int j, unsign
     f.rho = rho;
 }
 
+// ---- tiled dense records: implicit coordinates -------------------------------------------------------------------------
+// Per-lane constants of one tile (= ring stage): the lane's row, and the part of the folded warp that does not depend on the
+// word (column) or on the inverse depth: [Ub Vb Wb] = M[:, 0] a0 + M[:, 1] b + M[:, 2] with a0 = x0 - cx of the tile's first
+// column and b = y - cy of the lane's row.  Word j then costs two FFMAs per row of the matrix: M[:, 0] j + . and M[:, 3] rho + .
+struct TileLane {
+    float a0, b, Ub, Vb, Wb;
+    float M0v, M4v, M8v;
+};
+// front of word j of a tile (tiled records only exist for zero skew, plain L2: see AlignParams::tiled).
+// `tmpl`: the slot's template value; travels in Front::pk as f32 bits.
+template <int J>
+__device__ __forceinline__ void tile_front(const TileLane& t, float rho, uint32_t gr, float tmpl, const float (&M)[12], int word,
+                                           unsigned old_words, unsigned old_nz, const PassConst& lc, const Intrinsics& k, Defer& df,
+                                           float* hs, int lane, Front& f) {
+    // (M0v, M4v, M8v: the first matrix column in ordinary registers - an FFMA takes one uniform-register or immediate operand,
+    // and the word index J is the immediate)
+    const float U = fmaf(M[3], rho, J ? fmaf(t.M0v, float(J), t.Ub) : t.Ub);
+    const float V = fmaf(M[7], rho, J ? fmaf(t.M4v, float(J), t.Vb) : t.Vb);
+    const float W = fmaf(M[11], rho, J ? fmaf(t.M8v, float(J), t.Wb) : t.Wb);
+    const float iw = rcp_approx(W);
+    float u = fmaf(U, iw, lc.cx), v = fmaf(V, iw, lc.cy);
+    const float a = t.a0 + float(J);
+    // lm_optimizer.rs:231: inside iff 0 <= floor(u) < W-2 and 0 <= floor(v) < H-2; here: inside with a margin of kBandPx
+    const bool ok = (fabsf(u - lc.hu) < lc.lo_u) & (fabsf(v - lc.hv) < lc.lo_v);
+    const unsigned not_ok = __ballot_sync(0xffffffffu, !ok);
+    if (not_ok | (old_nz & (1u << J))) {  // warp-uniform, rare
+        const unsigned old_far = __shfl_sync(0xffffffffu, old_words, J);
+        rare_slots<false, false>(not_ok, u, v, rho, gr, a, t.b, word, old_far, lc, k, df, hs, lane);
+        if (!ok) {
+            u = lc.zero_u;
+            v = lc.zero_v;
+            tmpl = 0.0f;
+            rho = 0.0f;
+            gr = 0u;
+        }
+    }
+    sample_front(u, v, lc, f);
+    f.pk = __float_as_uint(tmpl);
+    f.gr = gr;
+    f.a = a;
+    f.b = t.b;
+    f.rho = rho;
+}
+__device__ __forceinline__ void tile_back(const Front& f, Acc<false>& acc) {
+    const float r = residual_of(f, __uint_as_float(f.pk));
+    acc.e = fmaf(r, r, acc.e);
+    accumulate_moments(acc, rec_gx(f.gr), rec_gy(f.gr), f.a, f.b, f.rho, r);
+}
+__device__ __forceinline__ float half_lo(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))); }
+__device__ __forceinline__ float half_hi(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
+
 // back: bilinear sample, residual, accumulate.
 template <bool kSkew, bool kHuber>
 __device__ __forceinline__ void back(const Front& f, const Intrinsics& k, float huber_delta, Acc<kHuber>& acc) {
     const float gu = rec_gx(f.gr), gv = rec_gy(f.gr);
-    const float a = f.fa, b = f.fb;
-    // bilinear sample in lerp form: the same interpolant as lm_optimizer.rs:241-246 (a along x, b along y) with 6 instead of
-    // 10 operations; it differs from the reference's four-product expression by ~1 ulp of the value, far inside the 1e-5
-    // bar on the pass energy (tests/test_gpu_parity.py)
-    const float t00 = u2f(f.t00), t10 = u2f(f.t10);
-    const float top = fmaf(a, u2f(f.t01) - t00, t00), bot = fmaf(a, u2f(f.t11) - t10, t10);
-    const float val = fmaf(b, bot - top, top);
-    const float r = val - u2f(f.pk >> 24);
+    const float r = residual_of(f, u2f(f.pk >> 24));
     if constexpr (kHuber) {
         float J[6];
         jacobian_centred<kSkew>(gu, gv, f.a, f.b, f.rho, k, J);
@@ -717,7 +859,7 @@ __device__ __forceinline__ float warp_matrix_entry(int e, const Pose& m, const L
     return float(r == 0 ? fx * a0 + s * a1 : r == 1 ? fy * a1 : a2);
 }
 
-template <bool kSkew, bool kHuber>
+template <bool kSkew, bool kHuber, bool kTiled>
 #ifdef VORS_MAXREG
 __global__ void __maxnreg__(VORS_MAXREG) k_align(const AlignParams P) {
 #else
@@ -763,7 +905,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
             const LevelJob& lj = job.lv[lvl];
             const int n = __shfl_sync(0xffffffffu, *lj.n_ptr, 0);
             const uint32_t* __restrict__ pts = lj.pts;
-            const int n_stages = (n + kStageCand - 1) / kStageCand;
+            const int n_stages = kTiled ? __shfl_sync(0xffffffffu, lj.n_tiles, 0) : (n + kStageCand - 1) / kStageCand;
             const int TW = team * kWarps;
             if (tid < kWarps * 21) (&S.hout[0][0])[tid] = 0.0;
             if (tid >= 32 && tid < 32 + 21) S.h_total[tid - 32] = lj.h_total[tid - 32];
@@ -785,6 +927,11 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                 c.zero_v = lj.zero_v;
                 c.rows = uint32_t(lj.rows);
                 c.n = n;
+                c.tex_ku = lj.tex_ku;
+                c.tex_kv = lj.tex_kv;
+                c.tex = job.tex;
+                c.tiles_y = lj.tiles_y;
+                c.inv_tiles_y = 1.0f / float(lj.tiles_y > 0 ? lj.tiles_y : 1);
                 choose_floor_magic(c, lj.img);
                 c.img = lj.img;
                 c.pts = pts;
@@ -816,6 +963,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                     lc.cx = s_lc.cx; lc.cy = s_lc.cy; lc.hu = s_lc.hu; lc.hv = s_lc.hv; lc.lo_u = s_lc.lo_u; lc.lo_v = s_lc.lo_v;
                     lc.magic_u = s_lc.magic_u; lc.magic_v = s_lc.magic_v; lc.rows = s_lc.rows; lc.img_biased = s_lc.img_biased;
                     lc.zero_u = s_lc.zero_u; lc.zero_v = s_lc.zero_v;
+                    lc.tex_ku = s_lc.tex_ku; lc.tex_kv = s_lc.tex_kv; lc.tex = s_lc.tex;
                     const Intrinsics k = s_lc.k;
                     constexpr int kNumS = kHuber ? 27 : kNumMoments;  // per-thread sums besides the energy
                     const float huber_delta = s_lc.huber_delta;
@@ -839,9 +987,94 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                     // with a candidate that reads nothing and contributes exact zeros.
                     Front fa, fb;
                     fb.pk = 0u; fb.gr = 0u; fb.a = 0.0f; fb.b = 0.0f; fb.rho = 0.0f; fb.fa = 0.0f; fb.fb = 0.0f;
+#if VORS_TEX
+                    fb.t00 = fb.t10 = fb.t01 = fb.t11 = 0.0f;
+#else
                     fb.t00 = fb.t10 = fb.t01 = fb.t11 = 0u;
+#endif
                     const int n_words = n_stages * kStageWordsBm;  // 32-slot words of the level (padding included)
-                    if (n_words <= kSmallWordsPerWarp * TW) {
+                    if constexpr (kTiled) {
+                        // ---- tiled dense records: every warp streams whole tiles (32 rows x 8 columns = one 2560-byte
+                        // stage, one bulk copy) through its ring; a lane owns one row of the tile, a word one column
+                        const int tiles_y = s_lc.tiles_y;
+                        if (lane == 0) {
+                            uint32_t slot = ring_slot;
+                            for (int j = 0, c = gw; j < kStages - 1 && c < n_stages; ++j, c += TW) {
+                                const uint32_t bar = bar_base + slot * 8u;
+                                mbar_expect_tx(bar, kTileBytes);
+                                bulk_g2s(ring_base + slot * kStageBytes, pts + size_t(c) * kTileWords, kTileBytes, bar, l2_policy);
+                                slot = (slot + 1 == kStages) ? 0u : slot + 1;
+                            }
+                        }
+                        if (df.first_pass) {  // the level's far bitmap starts empty: clear the words of this warp's tiles
+                            for (int c = gw; c < n_stages; c += TW)
+                                if (lane < kStageWordsBm) df.far[kStageWordsBm * c + lane] = 0u;
+                            __syncwarp();
+                        }
+                        const bool far_lane = lane < kStageWordsBm && !df.first_pass;
+                        const unsigned* far_ptr = df.far + (kStageWordsBm * gw + lane);
+                        const int far_step = kStageWordsBm * TW;
+                        unsigned old_next = (far_lane && gw < n_stages) ? __ldcg(far_ptr) : 0u;
+                        // tile (tx, ty) of stage c = tx * tiles_y + ty, advanced by TW stages per iteration
+                        int tx = gw / tiles_y, ty = gw - tx * tiles_y;
+                        const int dtx = TW / tiles_y, dty = TW - dtx * tiles_y;
+                        const float lane_f = float(lane);
+                        TileLane tl;
+        // thread-dependent on paper (threadIdx.y is 0 in every thread of this 1-D block, which the compiler cannot
+                        // know), so that these values live in ordinary registers instead of uniform ones
+                        const int zero_y = threadIdx.y;
+                        tl.M0v = S.M[0 + zero_y];
+                        tl.M4v = S.M[4 + zero_y];
+                        tl.M8v = S.M[8 + zero_y];
+                        for (int c = gw; c < n_stages; c += TW) {
+                            const int c_ahead = c + (kStages - 1) * TW;
+                            if (lane == 0 && c_ahead < n_stages) {
+                                const uint32_t slot = (ring_slot + kStages - 1 >= kStages) ? ring_slot - 1 : ring_slot + kStages - 1;
+                                const uint32_t bar = bar_base + slot * 8u;
+                                mbar_expect_tx(bar, kTileBytes);
+                                bulk_g2s(ring_base + slot * kStageBytes, pts + size_t(c_ahead) * kTileWords, kTileBytes, bar, l2_policy);
+                            }
+                            // per-lane constants of the tile while the bytes land
+                            tl.a0 = float(kTileCols * tx + zero_y) - lc.cx;  // camera.rs:135-140 starts from these rounded differences too
+                            tl.b = (float(kTileRows * ty) + lane_f) - lc.cy;  // (integers: the sum is exact)
+                            tl.Ub = fmaf(M[1], tl.b, fmaf(tl.M0v, tl.a0, M[2]));
+                            tl.Vb = fmaf(M[5], tl.b, fmaf(tl.M4v, tl.a0, M[6]));
+                            tl.Wb = fmaf(M[9], tl.b, fmaf(tl.M8v, tl.a0, M[10]));
+                            mbar_wait(bar_base + ring_slot * 8u, ring_parity);  // TMA bytes have landed
+                            const unsigned old_words = old_next;
+                            const unsigned old_nz = __ballot_sync(0xffffffffu, old_words != 0u);
+                            far_ptr += far_step;
+                            if (far_lane && c + TW < n_stages) old_next = __ldcg(far_ptr);
+                            const float4* s4 = reinterpret_cast<const float4*>(&S.ring[warp][ring_slot * kStageWords]);
+                            const uint4* u4 = reinterpret_cast<const uint4*>(s4);
+                            const float4 r0 = s4[lane], r1 = s4[32 + lane];         // inverse depths of words 0-3, 4-7
+                            const uint4 g0 = u4[64 + lane], g1 = u4[96 + lane];      // gradients (half2)
+                            const uint4 tm = u4[128 + lane];                         // template values (f16 x 8)
+                            const int w0 = kStageWordsBm * c;
+#define VORS_TSTEP(J, RHO, GR, TMPL, FNEW, FOLD)                                                                            \
+    tile_front<J>(tl, RHO, GR, TMPL, M, w0 + (J), old_words, old_nz, lc, k, df, hs, lane, FNEW);                            \
+    tile_back(FOLD, acc);
+                            VORS_TSTEP(0, r0.x, g0.x, half_lo(tm.x), fa, fb)
+                            VORS_TSTEP(1, r0.y, g0.y, half_hi(tm.x), fb, fa)
+                            VORS_TSTEP(2, r0.z, g0.z, half_lo(tm.y), fa, fb)
+                            VORS_TSTEP(3, r0.w, g0.w, half_hi(tm.y), fb, fa)
+                            VORS_TSTEP(4, r1.x, g1.x, half_lo(tm.z), fa, fb)
+                            VORS_TSTEP(5, r1.y, g1.y, half_hi(tm.z), fb, fa)
+                            VORS_TSTEP(6, r1.z, g1.z, half_lo(tm.w), fa, fb)
+                            VORS_TSTEP(7, r1.w, g1.w, half_hi(tm.w), fb, fa)
+#undef VORS_TSTEP
+                            __syncwarp();  // all lanes are done with this slot: the next iteration may refill it
+                            ring_slot = (ring_slot + 1 == kStages) ? 0u : ring_slot + 1;
+                            ring_parity ^= (ring_slot == 0) ? 1u : 0u;
+                            n_slots += kTileSlots;
+                            tx += dtx;
+                            ty += dty;
+                            if (ty >= tiles_y) {
+                                ty -= tiles_y;
+                                ++tx;
+                            }
+                        }
+                    } else if (n_words <= kSmallWordsPerWarp * TW) {
                         // ---- small level: a 256-candidate stage per warp would leave most warps idle and the rest with
                         // eight dependent word-steps, so the words are dealt round-robin to all warps and read straight from
                         // global memory (three coalesced loads per word); same front / back arithmetic, no pipelining.
@@ -919,7 +1152,10 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                             n_slots += kStageCand;
                         }
                     }
-                    back<kSkew, kHuber>(fb, k, huber_delta, acc);
+                    if constexpr (kTiled)
+                        tile_back(fb, acc);
+                    else
+                        back<kSkew, kHuber>(fb, k, huber_delta, acc);
 #if VORS_TIMING
                     const long long t_hot = clock64();
 #endif
@@ -937,7 +1173,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                     if (df.n_near > 0) {  // warp-uniform
                         int n_fix = 0;
                         Acc<kHuber> tmp = acc;  // only this copy has its address taken: `acc` itself stays in registers in the hot loop
-                        deferred_pass<kSkew, kHuber>(warp, lane, gw, TW, n_stages, lj.defer, df.wlist, df.n_words,
+                        deferred_pass<kSkew, kHuber, kTiled>(warp, lane, gw, TW, n_stages, lj.defer, df.wlist, df.n_words,
                                              reinterpret_cast<uint32_t*>(&S.ring[warp][0]), &tmp, &n_fix);
                         acc = tmp;
 #pragma unroll
@@ -1094,10 +1330,11 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
             __syncthreads();
             if (rank == 0) {
                 float s = 0.0f;
-                for (int i = tid; i < n; i += kConsumers) {
-                    const uint32_t p = lj.pts[pt_word(i, 0)];
-                    const float rho = __uint_as_float(lj.pts[pt_word(i, 1)]);
-                    const float x = float(rec_x(p)), y = float(rec_y(p));
+                const int n_slots_flow = kTiled ? lj.n_tiles * kTileSlots : n;
+                for (int i = tid; i < n_slots_flow; i += kConsumers) {
+                    const SlotRec sr = load_slot<kTiled>(lj.pts, lj.tiles_y, i);
+                    const float rho = sr.rho, x = sr.x, y = sr.y;
+                    if (kTiled && !(rho == rho)) continue;  // no depth / outside the image
                     const float U = fmaf(S.M[0], x, fmaf(S.M[1], y, fmaf(S.M[3], rho, S.M[2])));
                     const float V = fmaf(S.M[4], x, fmaf(S.M[5], y, fmaf(S.M[7], rho, S.M[6])));
                     const float W = fmaf(S.M[8], x, fmaf(S.M[9], y, fmaf(S.M[11], rho, S.M[10])));
@@ -1141,10 +1378,11 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
 
 template <typename F>
 static cudaError_t for_each_align_kernel(F f) {
-    cudaError_t e = f((const void*)k_align<false, false>);
-    if (e == cudaSuccess) e = f((const void*)k_align<true, false>);
-    if (e == cudaSuccess) e = f((const void*)k_align<false, true>);
-    if (e == cudaSuccess) e = f((const void*)k_align<true, true>);
+    cudaError_t e = f((const void*)k_align<false, false, false>);
+    if (e == cudaSuccess) e = f((const void*)k_align<true, false, false>);
+    if (e == cudaSuccess) e = f((const void*)k_align<false, true, false>);
+    if (e == cudaSuccess) e = f((const void*)k_align<true, true, false>);
+    if (e == cudaSuccess) e = f((const void*)k_align<false, false, true>);
     return e;
 }
 
@@ -1181,8 +1419,10 @@ cudaError_t launch_align(Launcher& L, const AlignParams& p, int n_teams) {
     cudaError_t e = align_prepare();
     if (e != cudaSuccess) return e;
     const bool huber = p.huber_delta > 0.0f;
-    const void* fn = huber ? (p.has_skew ? (const void*)k_align<true, true> : (const void*)k_align<false, true>)
-                           : (p.has_skew ? (const void*)k_align<true, false> : (const void*)k_align<false, false>);
+    if (p.tiled && (huber || p.has_skew)) return cudaErrorInvalidValue;  // tiled records exist for zero skew, plain L2 only
+    const void* fn = p.tiled ? (const void*)k_align<false, false, true>
+                   : huber   ? (p.has_skew ? (const void*)k_align<true, true, false> : (const void*)k_align<false, true, false>)
+                             : (p.has_skew ? (const void*)k_align<true, false, false> : (const void*)k_align<false, false, false>);
     void* args[] = {(void*)&p};
     if (p.team > 1)  // co-residency of a team's CTAs is required by the counter barrier: cooperative launch checks it
         return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kBlock), args, sizeof(LmShared), L.stream);

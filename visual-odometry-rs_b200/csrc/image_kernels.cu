@@ -13,6 +13,10 @@ namespace {
 
 __device__ __forceinline__ int item_of(const int* items, int j) { return items ? items[j] : j; }
 
+struct LevelIntrinsics {
+    Intrinsics k[kMaxLevels];
+};
+
 // ------------------------------------------------------------------------------------------------
 // Row-major (decoder output) -> column-major (internal, nalgebra) transposition; what
 // `DMatrix::from_row_slice` does on the CPU in the reference (src/misc/interop.rs:53-56).
@@ -410,9 +414,6 @@ __global__ void __launch_bounds__(kCompactBlock) k_compact_scatter(const Geom g,
 }  // namespace
 
 namespace {
-struct LevelIntrinsics {
-    Intrinsics k[kMaxLevels];
-};
 
 // Sum over ALL candidates of a level of J J^T (21 unique entries), once per keyframe.  The align kernel then
 // only accumulates J J^T for the candidates that fall OUTSIDE the frame in a pass and forms
@@ -487,6 +488,127 @@ __global__ void k_lie(int op, const float* __restrict__ in, float* __restrict__ 
     } else if (op == 3) {
         const Vec3 w = so3_log(Quat{in[0], in[1], in[2], in[3]});
         out[0] = w.x; out[1] = w.y; out[2] = w.z;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tiled dense records (vors_device.cuh): one CTA of 256 threads writes one tile = one 2560-byte ring stage of the align
+// kernel, slot (j, lane) = pixel (x = 8 tx + j, y = 32 ty + lane) of the tile's level.  No compaction: a pixel outside the
+// image or without a known inverse depth gets a NaN inverse depth (extract_z, inverse_compositional.rs:260-279, keeps
+// exactly the pixels whose inverse depth is known; here they keep their place and the others are marked).
+__device__ __forceinline__ int level_of_tile(const Geom& g, int tile) {
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < kMaxLevels; ++k)
+        if (k < g.L && tile >= g.tile_off[k]) l = k;
+    return l;
+}
+
+__global__ void __launch_bounds__(kTileSlots) k_tile_records(const Geom g, const float* __restrict__ idepth_slab,
+                                                             const uint8_t* __restrict__ pyr_slab,
+                                                             const uint32_t* __restrict__ grad_slab, uint32_t* __restrict__ pts_slab,
+                                                             const int* __restrict__ items) {
+    const int it = item_of(items, blockIdx.y);
+    const size_t base = size_t(it) * g.pix_stride;
+    const int tile = blockIdx.x, l = level_of_tile(g, tile);
+    const int t = tile - g.tile_off[l], tx = t / g.tiles_y[l], ty = t - tx * g.tiles_y[l];
+    const int j = threadIdx.x / kTileRows, lane = threadIdx.x % kTileRows;
+    const int x = kTileCols * tx + j, y = kTileRows * ty + lane;
+    const int R = g.rows[l], C = g.cols[l];
+    float rho = __int_as_float(0x7fc00000);
+    uint32_t gr = 0u;
+    unsigned short tm = 0;
+    if (x < C && y < R) {
+        const size_t src = base + g.off[l] + size_t(x) * R + y;
+        const float d = idepth_slab[src];
+        if (!isnan(d)) {
+            rho = d;
+            gr = rec_pack_grad(grad_slab[src]);
+            tm = __half_as_ushort(__float2half_rn(float(pyr_slab[src])));  // 0..255: exact in f16
+        }
+    }
+    uint32_t* st = pts_slab + (size_t(it) * g.tile_total + tile) * kTileWords;
+    st[tile_rho_word(j, lane)] = __float_as_uint(rho);
+    st[tile_grad_word(j, lane)] = gr;
+    reinterpret_cast<unsigned short*>(st)[tile_tmpl_half(j, lane)] = tm;
+}
+
+// Row K for tiled records: sum of J J^T over the level's valid slots (f64, fixed order) and their count (-> n_points).
+__global__ void __launch_bounds__(512) k_h_total_tiled(const Geom g, const LevelIntrinsics li, const uint32_t* __restrict__ pts_slab,
+                                                       int* __restrict__ n_points, double* __restrict__ h_total,
+                                                       const int* __restrict__ items) {
+    __shared__ double part[16][21];
+    __shared__ int cnt[16];
+    const int it = item_of(items, blockIdx.y), l = blockIdx.x;
+    const uint32_t* lvl = pts_slab + (size_t(it) * g.tile_total + g.tile_off[l]) * kTileWords;
+    const int n_slots = g.tiles_y[l] * g.tiles_x[l] * kTileSlots, tiles_y = g.tiles_y[l];
+    const Intrinsics k = li.k[l];
+    double acc[21];
+#pragma unroll
+    for (int c = 0; c < 21; ++c) acc[c] = 0.0;
+    int valid = 0;
+    for (int i = threadIdx.x; i < n_slots; i += blockDim.x) {
+        const int st = i / kTileSlots, j = (i / kTileRows) % kTileCols, ln = i % kTileRows;
+        const uint32_t* w = lvl + size_t(st) * kTileWords;
+        const float rho = __uint_as_float(w[tile_rho_word(j, ln)]);
+        if (isnan(rho)) continue;
+        ++valid;
+        const int tx = st / tiles_y, ty = st - tx * tiles_y;
+        const uint32_t gr = w[tile_grad_word(j, ln)];
+        float J[6];
+        jacobian_at<true>(rec_gx(gr), rec_gy(gr), float(kTileCols * tx + j), float(kTileRows * ty + ln), rho, k, J);
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = a; b < 6; ++b, ++t) acc[t] += double(J[a]) * double(J[b]);  // exact in f64
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < 21; ++c) {
+        double v = acc[c];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if (lane == 0) part[w][c] = v;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, d);
+    if (lane == 0) cnt[w] = valid;
+    __syncthreads();
+    if (threadIdx.x < 21) {
+        double s = 0.0;
+        for (int ww = 0; ww < int(blockDim.x >> 5); ++ww) s += part[ww][threadIdx.x];
+        h_total[(size_t(it) * kMaxLevels + l) * kHStride + threadIdx.x] = s;
+    }
+    if (threadIdx.x == 32) {
+        int s = 0;
+        for (int ww = 0; ww < int(blockDim.x >> 5); ++ww) s += cnt[ww];
+        n_points[it * kMaxLevels + l] = s;
+    }
+}
+
+// Frame pyramids -> atlas page (vors_device.cuh): every level of every listed stream, through surface stores.
+// Texture x = image row (the fast axis of the column-major pyramid): consecutive threads write consecutive texels.
+__global__ void k_atlas_fill(const Geom g, const uint8_t* __restrict__ pyr_slab, const AtlasPages pages, const int* __restrict__ items,
+                             int first) {
+    // stream `it`; its slab sits at index items[j] of pyr_slab, or at index j when pyr_slab already points at stream `first`
+    const int it = items ? items[blockIdx.y] : first + int(blockIdx.y);
+    const uint8_t* pyr = pyr_slab + size_t(items ? items[blockIdx.y] : int(blockIdx.y)) * g.pix_stride;
+    const int page = it / g.per_page, cell = it - page * g.per_page;
+    const int ox = (cell % g.per_row) * g.cell_w, oy = (cell / g.per_row) * g.cell_h;
+    const cudaSurfaceObject_t surf = pages.surf[page];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.pix_total; i += gridDim.x * blockDim.x) {
+        int l = 0;
+#pragma unroll
+        for (int k = 1; k < kMaxLevels; ++k)
+            if (k < g.L && i >= g.off[k]) l = k;
+        const int o = i - g.off[l];
+        const int R = g.rows[l];
+        const int x = o / R, y = o - x * R;
+        if (pages.f16)
+            surf2Dwrite<unsigned short>(__half_as_ushort(__float2half_rn(float(pyr[i]))), surf, (ox + y) * 2, oy + g.lvl_y[l] + x);
+        else
+            surf2Dwrite<unsigned char>(pyr[i], surf, ox + y, oy + g.lvl_y[l] + x);
     }
 }
 
@@ -572,6 +694,21 @@ void launch_h_total(Launcher& L, const Geom& g, const Intrinsics* intr, const ui
     for (int l = 0; l < kMaxLevels; ++l) li.k[l] = intr[l < g.L ? l : g.L - 1];
     dim3 grid(g.L, m);
     k_h_total<<<grid, 512, 0, L.stream>>>(g, li, pts_slab, n_points, h_total, items);
+    ++L.launches;
+}
+void launch_tile_records(Launcher& L, const Geom& g, const Intrinsics* intr, const float* idepth_slab, const uint8_t* pyr_slab,
+                          const uint32_t* grad_slab, int* n_points, uint32_t* pts_slab, double* h_total, const int* items, int m) {
+    dim3 grid(g.tile_total, m);
+    k_tile_records<<<grid, kTileSlots, 0, L.stream>>>(g, idepth_slab, pyr_slab, grad_slab, pts_slab, items);
+    LevelIntrinsics li;
+    for (int l = 0; l < kMaxLevels; ++l) li.k[l] = intr[l < g.L ? l : g.L - 1];
+    dim3 gridh(g.L, m);
+    k_h_total_tiled<<<gridh, 512, 0, L.stream>>>(g, li, pts_slab, n_points, h_total, items);
+    L.launches += 2;
+}
+void launch_atlas_fill(Launcher& L, const Geom& g, const uint8_t* pyr_slab, const AtlasPages& pages, const int* items, int m, int first) {
+    dim3 grid(grid_for(g.pix_total, 256, 64), m);
+    k_atlas_fill<<<grid, 256, 0, L.stream>>>(g, pyr_slab, pages, items, first);
     ++L.launches;
 }
 void launch_jacobians(Launcher& L, const uint32_t* pts_level, int n, Intrinsics k, float* out6) {

@@ -12,6 +12,18 @@
 //   * n streams (trackers) of a batch own consecutive slabs: base + stream * pix_stride (pt_total for candidates);
 //     pix_stride = pix_total + a zero page of rows_0 + 2 bytes (rounded up to 16) that is never written in the
 //     frame-pyramid slab: the align kernel points candidates that fall outside the frame at it (all four texels 0).
+//   * DENSE keyframes with zero skew and plain L2 (the benchmarked configuration) use TILED records with IMPLICIT coordinates
+//     instead: a level is cut into tiles of 32 rows x 8 columns; one tile = one ring stage of 256 slots, slot (j, lane) =
+//     pixel (x = 8 tx + j, y = 32 ty + lane), tiles ordered column-of-tiles major (stage c = tx * tiles_y + ty).  A stage is
+//     2560 bytes: inverse depths f32 [2][32][4] (lane-contiguous quads: one 16-byte shared load brings four words' values),
+//     gradients half2 [2][32][4], template values f16 [32][8] = 10 B per slot; pixels outside the image or without depth
+//     carry a NaN inverse depth (never inside, never in H_total).  x, y never travel: they follow from the stage and lane.
+//   * the frame pyramids the align kernel SAMPLES live in gather-enabled 2D CUDA arrays ("atlas pages", u8 texels read as
+//     texel / 255, or f16 with -DVORS_TEX_F16=1): texture x = image y.  Stream s, level l occupies the cell at
+//     (ox, oy) = ((s % per_row) * cell_w, (s / per_row) * cell_h + lvl_y[l]) with cell_w = rows_0 + 2, lvl_y[l] = sum_{k<l}
+//     (cols_k + 2): the two texels after every level's last row / column are never written (zero) and serve as the zero page.
+//     One tld4 returns the 2x2 footprint of a warped candidate.  The linear pyramids stay: keyframe build and the exact
+//     re-evaluation of boundary-band candidates read them.
 #pragma once
 
 #include <cuda_fp16.h>
@@ -20,6 +32,15 @@
 
 #include "../../include/vors_b200.h"
 #include "lie.cuh"
+
+// compile-time variants (scripts/build_variants.sh passes them to every translation unit)
+#ifndef VORS_TEX
+#define VORS_TEX 1      // 1: the align kernel samples the current frame with one texture gather (tld4) per candidate from the
+                        // atlas pages; 0: four byte loads from the linear pyramid
+#endif
+#ifndef VORS_TEX_F16
+#define VORS_TEX_F16 0  // atlas texels: 0 = u8 read as texel / 255 (normalised float), 1 = f16 (exact values, twice the bytes)
+#endif
 
 namespace vors {
 
@@ -36,6 +57,13 @@ constexpr int kHStride = 24;         // doubles per (stream, level) in the H_tot
 constexpr int kNumAcc = 29;          // finished pass: sum r^2, n_inside, g[6], H[21] (upper triangle)
 constexpr int kNumRaw = 32;          // raw pass accumulators: sum r^2, n_inside, 9 gradient moments (or g[6]), H_outside[21]
 
+constexpr int kTileRows = 32;        // tiled dense records: a tile is 32 rows (lanes) x kTileCols columns (words of a stage)
+constexpr int kTileCols = 8;
+constexpr int kTileSlots = kTileRows * kTileCols;
+constexpr int kTileBytes = kTileSlots * 10;  // rho f32 | grad half2 | template f16
+constexpr int kTileWords = kTileBytes / 4;
+static_assert(kTileSlots == VORS_STAGE_CHUNKS * 64, "a tile is one ring stage of the align kernel");
+
 struct Geom {
     int L;
     int rows[kMaxLevels], cols[kMaxLevels];
@@ -46,7 +74,20 @@ struct Geom {
     int pix_total;               // pixels of all levels
     int pix_stride;              // per-stream slab stride: pix_total + zero page (see above)
     int blk_total;
+    // tiled dense records (see the header comment)
+    int tiles_y[kMaxLevels], tiles_x[kMaxLevels];
+    int tile_off[kMaxLevels];    // first tile (= stage) of level l inside a stream's tiled record slab
+    int tile_total;              // tiles per stream
+    // texture atlas cell of one stream
+    int cell_w, cell_h;          // rows_0 + 2, sum (cols_l + 2)
+    int lvl_y[kMaxLevels];       // texel row of level l inside the cell
+    int per_row, per_page;       // cells per atlas row / per atlas page
 };
+
+// word offsets of slot (j, lane) of a tile inside its 640-word stage
+__host__ __device__ __forceinline__ int tile_rho_word(int j, int lane) { return (j >> 2) * 128 + lane * 4 + (j & 3); }
+__host__ __device__ __forceinline__ int tile_grad_word(int j, int lane) { return 256 + tile_rho_word(j, lane); }
+__host__ __device__ __forceinline__ int tile_tmpl_half(int j, int lane) { return 1024 + lane * 8 + j; }  // index in halves
 
 // ---- candidate record fields -----------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint32_t rec_pack_pk(int x, int y, uint32_t tmpl) { return uint32_t(x) | (uint32_t(y) << 12) | (tmpl << 24); }
@@ -66,7 +107,7 @@ __device__ __forceinline__ float rec_gy(uint32_t gr) { return __half2float(__ush
 __host__ __device__ __forceinline__ size_t pt_word(int i, int f) { return size_t(i / kChunk) * (3 * kChunk) + size_t(f) * kChunk + size_t(i % kChunk); }
 
 struct LevelJob {
-    const uint32_t* pts;  // chunk-blocked candidates of this level
+    const uint32_t* pts;  // chunk-blocked candidates of this level (tiled dense keyframes: the level's tiles, kTileWords each)
     const uint8_t* img;  // current frame, this level
     const int* n_ptr;    // number of candidates (device memory: written by the compaction kernels)
     const double* h_total;  // sum over ALL candidates of J J^T, 21 upper-triangle entries (k_h_total)
@@ -74,6 +115,8 @@ struct LevelJob {
     uint32_t* defer_far; // same, for the slots it found outside for sure
     int rows, cols;
     float zero_u, zero_v;  // integer-valued image coordinates whose 2x2 footprint is the slab's zero page
+    float tex_ku, tex_kv;  // texture path: (2^23 + floor(u)) - tex_ku = atlas texel row of the footprint's shared corner (same for v)
+    int tiles_y, n_tiles;  // tiled dense records: tiles per tile column, tiles of the level
     Intrinsics k;
 };
 
@@ -83,6 +126,7 @@ struct AlignJob {
     int lvl_last;     // finest level to run (0)
     int flow_level;   // level whose candidates feed the optical-flow test (nb_levels-1); <0 = skip
     int pass_only;    // 1: single evaluation at `init` on lvl_first, no LM loop (vors_align_pass)
+    unsigned long long tex;  // cudaTextureObject_t of the atlas page holding this stream's current frame pyramid
 };
 
 struct AlignResult {
@@ -120,6 +164,7 @@ struct AlignParams {
     float lm_coef_init, lm_coef_reject_mult, lm_coef_accept_mult, energy_delta_stop;
     int max_iters, fixed_iters;
     int has_skew;  // 0 selects the zero-skew Jacobian specialisation
+    int tiled;     // 1: the keyframes hold tiled dense records with implicit coordinates (dense, zero skew, plain L2)
     float huber_delta;  // > 0 selects the Huber-weighted kernel variant (extension)
 };
 
@@ -184,6 +229,17 @@ void launch_compact(Launcher& L, const Geom& g, const float* idepth_slab, const 
                     int* blk_count, int* n_points, uint32_t* pts_slab, const int* items, int m);
 void launch_h_total(Launcher& L, const Geom& g, const Intrinsics* intr, const uint32_t* pts_slab, const int* n_points,
                     double* h_total, const int* items, int m);
+// tiled dense keyframes: records + H_total + candidate counts of all levels (replaces launch_compact + launch_h_total)
+void launch_tile_records(Launcher& L, const Geom& g, const Intrinsics* intr, const float* idepth_slab, const uint8_t* pyr_slab,
+                         const uint32_t* grad_slab, int* n_points, uint32_t* pts_slab, double* h_total, const int* items, int m);
+// linear frame pyramids of m streams (items, or first .. first + m - 1 when items == nullptr and pyr_slab points at stream
+// `first`'s slab) -> their cells of the atlas pages
+constexpr int kMaxAtlasPages = 8;
+struct AtlasPages {
+    cudaSurfaceObject_t surf[kMaxAtlasPages];
+    int f16;
+};
+void launch_atlas_fill(Launcher& L, const Geom& g, const uint8_t* pyr_slab, const AtlasPages& pages, const int* items, int m, int first);
 void launch_jacobians(Launcher& L, const uint32_t* pts_level, int n, Intrinsics k, float* out6);
 void launch_se3_exp(Launcher& L, const float* xi6, Pose* out);
 void launch_lie(Launcher& L, int op, const float* in, float* out);
