@@ -44,7 +44,7 @@ def main():
             t = int(m.group(2), 16)
             body = [y for (b, y) in ins if t <= b <= a]
             gathers = sum("LDG.E.U8" in y for y in body), sum("TLD4" in y for y in body)
-            if gathers in ((32, 0), (0, 8)) and any("UBLKCP" in y for y in body):  # byte loads, or -DVORS_TEX=1: one gather each
+            if gathers in ((32, 0), (0, 8), (0, 12)) and any("UBLKCP" in y for y in body):  # byte loads, or -DVORS_TEX=1: one gather each
                 loops.append((a - t, t, a))
     _, head, tail = min(loops)
     start, end = at[head], at[tail]
@@ -77,8 +77,9 @@ def main():
     for i in path:
         p = ins[i][1].split()
         ops[(p[1] if p[0].startswith("@") else p[0]).split(".")[0]] += 1
+    n_words = max(8, sum("TLD4" in ins[i][1] for i in path))  # words (= candidates per lane) per iteration: 8, or 12 tiled
     print(f"loop {head:#x}..{tail:#x}: {(tail - head) // 16 + 1} instructions in the body, common path {len(path)} "
-          f"= {len(path) / 8:.3f} per candidate; BRA.DIV on it: {sum('BRA.DIV' in ins[i][1] for i in path)}")
+          f"= {len(path) / n_words:.3f} per candidate ({n_words} per iteration); BRA.DIV on it: {sum('BRA.DIV' in ins[i][1] for i in path)}")
     print(sorted(ops.items(), key=lambda kv: -kv[1]))
     with open("/tmp/common.sass", "w") as f:
         f.write("\n".join(f"{ins[i][0]:05x} {ins[i][1]}" for i in path))

@@ -70,7 +70,10 @@ constexpr int kStageWordsBm = kStageCand / 32;     // bitmap words per stage
 constexpr int kStages = VORS_STAGES;          // TMA ring depth per warp
 constexpr int kStageWords = kStageChunks * 3 * kChunk;  // per chunk: pk[64] | idepth[64] | grad[64]
 constexpr uint32_t kStageBytes = kStageWords * 4;
-constexpr int kHsmStride = 28;
+constexpr int kRingWords = kStageWords > kTileWords ? kStageWords : kTileWords;  // ring slot: a stage of either record layout
+constexpr uint32_t kRingBytes = kRingWords * 4;
+constexpr int kTileWordsBm = kTileSlots / 32;  // bitmap words per tile
+constexpr int kHsmStride = 21;  // odd: scalar accesses of a warp hit 32 distinct banks
 static_assert(kStageCand == kPtAlign, "levels are padded to whole ring stages");
 
 struct LmShared {
@@ -103,9 +106,10 @@ struct LmShared {
 #endif
     uint32_t near_words[kWarps][2 * 32];  // (word, mask) pairs flagged for deferred_pass by each warp in this pass
     alignas(8) unsigned long long full_bar[kWarps][kStages];
-    alignas(128) float ring[kWarps][kStages * kStageWords];
-    // per-thread J J^T accumulators of the hot loop (candidates that changed sides of the frame border): 21 floats at a
-    // 28-word stride (16-byte vector accesses of a quarter warp then hit 8 distinct bank groups); zero between passes
+    alignas(128) float ring[kWarps][kStages * kRingWords];
+    // per-thread J J^T accumulators of the hot loop (candidates that changed sides of the frame border): 21 floats at an
+    // odd stride (conflict-free scalar accesses; this rare path trades vector accesses for 9 KB of shared memory); zero
+    // between passes
     alignas(16) float hsm[kConsumers][kHsmStride];
 };
 
@@ -441,7 +445,7 @@ __device__ __noinline__ void deferred_pass(int warp, int lane, int first_stage, 
     } else {
         // more flagged words than remembered (e.g. a static camera: the x = 0 column and the y = 0 row sit exactly on the
         // inside-test boundary): scan this warp's part of the bitmap, one group of 128 slots (a uint4 of bitmap words) per lane
-        constexpr int kGroups = kStageCand / 128;
+        constexpr int kGroups = (kTiled ? kTileSlots : kStageCand) / 128;
         const int my_groups = first_stage < n_stages ? ((n_stages - first_stage + stage_stride - 1) / stage_stride) * kGroups : 0;
         for (int g0 = 0; g0 < my_groups; g0 += 32) {  // warp-uniform trip count
             const int gi = g0 + lane;
@@ -546,13 +550,6 @@ struct Defer {
 // +-J J^T of this lane's candidate (`sign` = +1 / -1 / 0) added to the thread's shared-memory accumulators.
 template <bool kSkew>
 __device__ __forceinline__ void add_outside(float sign, uint32_t gr, float a, float b, float rho, const Intrinsics& k, float* hs) {
-    float4* h4 = reinterpret_cast<float4*>(hs);
-    float h[24];
-#pragma unroll
-    for (int q = 0; q < 6; ++q) {
-        const float4 t = h4[q];
-        h[4 * q] = t.x; h[4 * q + 1] = t.y; h[4 * q + 2] = t.z; h[4 * q + 3] = t.w;
-    }
     float J[6];
     // J is linear in the gradient: zero gradient (and a finite inverse depth: padding slots carry NaN) -> J = 0 exactly
     const bool on = sign != 0.0f;
@@ -561,10 +558,8 @@ __device__ __forceinline__ void add_outside(float sign, uint32_t gr, float a, fl
     for (int c = 0; c < 6; ++c) {
         const float jc = sign * J[c];
 #pragma unroll
-        for (int d = c; d < 6; ++d) h[tri(c, d)] = fmaf(jc, J[d], h[tri(c, d)]);
+        for (int d = c; d < 6; ++d) hs[tri(c, d)] = fmaf(jc, J[d], hs[tri(c, d)]);
     }
-#pragma unroll
-    for (int q = 0; q < 6; ++q) h4[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
 }
 
 // front, first half: unpack, warp, inside test - straight-line arithmetic that the compiler can interleave with the
@@ -992,9 +987,10 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
 #else
                     fb.t00 = fb.t10 = fb.t01 = fb.t11 = 0u;
 #endif
-                    const int n_words = n_stages * kStageWordsBm;  // 32-slot words of the level (padding included)
+                    Front f0 = fb, f1 = fb, f2 = fb;  // tiled records: three pipeline slots
+                    const int n_words = n_stages * (kTiled ? kTileWordsBm : kStageWordsBm);  // 32-slot words of the level (padding included)
                     if constexpr (kTiled) {
-                        // ---- tiled dense records: every warp streams whole tiles (32 rows x 8 columns = one 2560-byte
+                        // ---- tiled dense records: every warp streams whole tiles (32 rows x 12 columns = one 3840-byte
                         // stage, one bulk copy) through its ring; a lane owns one row of the tile, a word one column
                         const int tiles_y = s_lc.tiles_y;
                         if (lane == 0) {
@@ -1002,25 +998,25 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                             for (int j = 0, c = gw; j < kStages - 1 && c < n_stages; ++j, c += TW) {
                                 const uint32_t bar = bar_base + slot * 8u;
                                 mbar_expect_tx(bar, kTileBytes);
-                                bulk_g2s(ring_base + slot * kStageBytes, pts + size_t(c) * kTileWords, kTileBytes, bar, l2_policy);
+                                bulk_g2s(ring_base + slot * kRingBytes, pts + size_t(c) * kTileWords, kTileBytes, bar, l2_policy);
                                 slot = (slot + 1 == kStages) ? 0u : slot + 1;
                             }
                         }
                         if (df.first_pass) {  // the level's far bitmap starts empty: clear the words of this warp's tiles
                             for (int c = gw; c < n_stages; c += TW)
-                                if (lane < kStageWordsBm) df.far[kStageWordsBm * c + lane] = 0u;
+                                if (lane < kTileWordsBm) df.far[kTileWordsBm * c + lane] = 0u;
                             __syncwarp();
                         }
-                        const bool far_lane = lane < kStageWordsBm && !df.first_pass;
-                        const unsigned* far_ptr = df.far + (kStageWordsBm * gw + lane);
-                        const int far_step = kStageWordsBm * TW;
+                        const bool far_lane = lane < kTileWordsBm && !df.first_pass;
+                        const unsigned* far_ptr = df.far + (kTileWordsBm * gw + lane);
+                        const int far_step = kTileWordsBm * TW;
                         unsigned old_next = (far_lane && gw < n_stages) ? __ldcg(far_ptr) : 0u;
                         // tile (tx, ty) of stage c = tx * tiles_y + ty, advanced by TW stages per iteration
                         int tx = gw / tiles_y, ty = gw - tx * tiles_y;
                         const int dtx = TW / tiles_y, dty = TW - dtx * tiles_y;
                         const float lane_f = float(lane);
                         TileLane tl;
-        // thread-dependent on paper (threadIdx.y is 0 in every thread of this 1-D block, which the compiler cannot
+                        // thread-dependent on paper (threadIdx.y is 0 in every thread of this 1-D block, which the compiler cannot
                         // know), so that these values live in ordinary registers instead of uniform ones
                         const int zero_y = threadIdx.y;
                         tl.M0v = S.M[0 + zero_y];
@@ -1032,7 +1028,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                                 const uint32_t slot = (ring_slot + kStages - 1 >= kStages) ? ring_slot - 1 : ring_slot + kStages - 1;
                                 const uint32_t bar = bar_base + slot * 8u;
                                 mbar_expect_tx(bar, kTileBytes);
-                                bulk_g2s(ring_base + slot * kStageBytes, pts + size_t(c_ahead) * kTileWords, kTileBytes, bar, l2_policy);
+                                bulk_g2s(ring_base + slot * kRingBytes, pts + size_t(c_ahead) * kTileWords, kTileBytes, bar, l2_policy);
                             }
                             // per-lane constants of the tile while the bytes land
                             tl.a0 = float(kTileCols * tx + zero_y) - lc.cx;  // camera.rs:135-140 starts from these rounded differences too
@@ -1045,23 +1041,31 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                             const unsigned old_nz = __ballot_sync(0xffffffffu, old_words != 0u);
                             far_ptr += far_step;
                             if (far_lane && c + TW < n_stages) old_next = __ldcg(far_ptr);
-                            const float4* s4 = reinterpret_cast<const float4*>(&S.ring[warp][ring_slot * kStageWords]);
-                            const uint4* u4 = reinterpret_cast<const uint4*>(s4);
-                            const float4 r0 = s4[lane], r1 = s4[32 + lane];         // inverse depths of words 0-3, 4-7
-                            const uint4 g0 = u4[64 + lane], g1 = u4[96 + lane];      // gradients (half2)
-                            const uint4 tm = u4[128 + lane];                         // template values (f16 x 8)
-                            const int w0 = kStageWordsBm * c;
+                            const float* sp = &S.ring[warp][ring_slot * kRingWords];
+                            const float4* r4 = reinterpret_cast<const float4*>(sp) + lane;                    // inverse depths, 4 words each
+                            const uint4* g4 = reinterpret_cast<const uint4*>(sp + kTileSlots) + lane;          // gradients (half2)
+                            const uint2* t2 = reinterpret_cast<const uint2*>(sp + 2 * kTileSlots) + lane;      // template values (f16 x 4)
+                            const int w0 = kTileWordsBm * c;
+                            // software pipeline, three slots: word J's front (its texture gather) is issued two words before its
+                            // back, so two gathers per lane are in flight while a third word is being reduced
 #define VORS_TSTEP(J, RHO, GR, TMPL, FNEW, FOLD)                                                                            \
     tile_front<J>(tl, RHO, GR, TMPL, M, w0 + (J), old_words, old_nz, lc, k, df, hs, lane, FNEW);                            \
     tile_back(FOLD, acc);
-                            VORS_TSTEP(0, r0.x, g0.x, half_lo(tm.x), fa, fb)
-                            VORS_TSTEP(1, r0.y, g0.y, half_hi(tm.x), fb, fa)
-                            VORS_TSTEP(2, r0.z, g0.z, half_lo(tm.y), fa, fb)
-                            VORS_TSTEP(3, r0.w, g0.w, half_hi(tm.y), fb, fa)
-                            VORS_TSTEP(4, r1.x, g1.x, half_lo(tm.z), fa, fb)
-                            VORS_TSTEP(5, r1.y, g1.y, half_hi(tm.z), fb, fa)
-                            VORS_TSTEP(6, r1.z, g1.z, half_lo(tm.w), fa, fb)
-                            VORS_TSTEP(7, r1.w, g1.w, half_hi(tm.w), fb, fa)
+#define VORS_TQUAD(H, FA, FB, FC)                                                                                           \
+    {                                                                                                                       \
+        const float4 rq = r4[32 * (H)];                                                                                     \
+        const uint4 gq = g4[32 * (H)];                                                                                      \
+        const uint2 tq = t2[32 * (H)];                                                                                      \
+        VORS_TSTEP(4 * (H) + 0, rq.x, gq.x, half_lo(tq.x), FA, FB)                                                          \
+        VORS_TSTEP(4 * (H) + 1, rq.y, gq.y, half_hi(tq.x), FB, FC)                                                          \
+        VORS_TSTEP(4 * (H) + 2, rq.z, gq.z, half_lo(tq.y), FC, FA)                                                          \
+        VORS_TSTEP(4 * (H) + 3, rq.w, gq.w, half_hi(tq.y), FA, FB)                                                          \
+    }
+                            // word J fills slot J % 3 and consumes slot (J + 1) % 3 = word J - 2
+                            VORS_TQUAD(0, f0, f1, f2)
+                            VORS_TQUAD(1, f1, f2, f0)
+                            VORS_TQUAD(2, f2, f0, f1)
+#undef VORS_TQUAD
 #undef VORS_TSTEP
                             __syncwarp();  // all lanes are done with this slot: the next iteration may refill it
                             ring_slot = (ring_slot + 1 == kStages) ? 0u : ring_slot + 1;
@@ -1102,7 +1106,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                             for (int j = 0, c = gw; j < kStages - 1 && c < n_stages; ++j, c += TW) {
                                 const uint32_t bar = bar_base + slot * 8u;
                                 mbar_expect_tx(bar, kStageBytes);
-                                bulk_g2s(ring_base + slot * kStageBytes, pts + size_t(c) * kStageWords, kStageBytes, bar, l2_policy);
+                                bulk_g2s(ring_base + slot * kRingBytes, pts + size_t(c) * kStageWords, kStageBytes, bar, l2_policy);
                                 slot = (slot + 1 == kStages) ? 0u : slot + 1;
                             }
                         }
@@ -1124,14 +1128,14 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                                 const uint32_t slot = (ring_slot + kStages - 1 >= kStages) ? ring_slot - 1 : ring_slot + kStages - 1;
                                 const uint32_t bar = bar_base + slot * 8u;
                                 mbar_expect_tx(bar, kStageBytes);
-                                bulk_g2s(ring_base + slot * kStageBytes, pts + size_t(c_ahead) * kStageWords, kStageBytes, bar, l2_policy);
+                                bulk_g2s(ring_base + slot * kRingBytes, pts + size_t(c_ahead) * kStageWords, kStageBytes, bar, l2_policy);
                             }
                             mbar_wait(bar_base + ring_slot * 8u, ring_parity);  // TMA bytes have landed
                             const unsigned old_words = old_next;
                             const unsigned old_nz = __ballot_sync(0xffffffffu, old_words != 0u);
                             far_ptr += far_step;
                             if (far_lane && c + TW < n_stages) old_next = __ldcg(far_ptr);
-                            const float* sp = &S.ring[warp][ring_slot * kStageWords] + lane;
+                            const float* sp = &S.ring[warp][ring_slot * kRingWords] + lane;
                             // word j of the stage = 32 consecutive candidates (chunk j / 2, half j % 2), one per lane
 #define VORS_STEP(CH, HALF, FNEW, FOLD)                                                               \
     {                                                                                                 \
@@ -1152,10 +1156,12 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                             n_slots += kStageCand;
                         }
                     }
-                    if constexpr (kTiled)
-                        tile_back(fb, acc);
-                    else
+                    if constexpr (kTiled) {  // the last two words of the last tile (slots 10 % 3 and 11 % 3) are still in flight
+                        tile_back(f1, acc);
+                        tile_back(f2, acc);
+                    } else {
                         back<kSkew, kHuber>(fb, k, huber_delta, acc);
+                    }
 #if VORS_TIMING
                     const long long t_hot = clock64();
 #endif

@@ -13,11 +13,12 @@
 //     pix_stride = pix_total + a zero page of rows_0 + 2 bytes (rounded up to 16) that is never written in the
 //     frame-pyramid slab: the align kernel points candidates that fall outside the frame at it (all four texels 0).
 //   * DENSE keyframes with zero skew and plain L2 (the benchmarked configuration) use TILED records with IMPLICIT coordinates
-//     instead: a level is cut into tiles of 32 rows x 8 columns; one tile = one ring stage of 256 slots, slot (j, lane) =
-//     pixel (x = 8 tx + j, y = 32 ty + lane), tiles ordered column-of-tiles major (stage c = tx * tiles_y + ty).  A stage is
-//     2560 bytes: inverse depths f32 [2][32][4] (lane-contiguous quads: one 16-byte shared load brings four words' values),
-//     gradients half2 [2][32][4], template values f16 [32][8] = 10 B per slot; pixels outside the image or without depth
+//     instead: a level is cut into tiles of 32 rows x 12 columns; one tile = one ring stage of 384 slots, slot (j, lane) =
+//     pixel (x = 12 tx + j, y = 32 ty + lane), tiles ordered column-of-tiles major (stage c = tx * tiles_y + ty).  A stage is
+//     3840 bytes: inverse depths f32 [3][32][4] (lane-contiguous quads: one 16-byte shared load brings four words' values),
+//     gradients half2 [3][32][4], template values f16 [3][32][4] = 10 B per slot; pixels outside the image or without depth
 //     carry a NaN inverse depth (never inside, never in H_total).  x, y never travel: they follow from the stage and lane.
+//     (12 columns: a multiple of the three-deep software pipeline of the align kernel's hot loop.)
 //   * the frame pyramids the align kernel SAMPLES live in gather-enabled 2D CUDA arrays ("atlas pages", u8 texels read as
 //     texel / 255, or f16 with -DVORS_TEX_F16=1): texture x = image y.  Stream s, level l occupies the cell at
 //     (ox, oy) = ((s % per_row) * cell_w, (s / per_row) * cell_h + lvl_y[l]) with cell_w = rows_0 + 2, lvl_y[l] = sum_{k<l}
@@ -58,11 +59,11 @@ constexpr int kNumAcc = 29;          // finished pass: sum r^2, n_inside, g[6], 
 constexpr int kNumRaw = 32;          // raw pass accumulators: sum r^2, n_inside, 9 gradient moments (or g[6]), H_outside[21]
 
 constexpr int kTileRows = 32;        // tiled dense records: a tile is 32 rows (lanes) x kTileCols columns (words of a stage)
-constexpr int kTileCols = 8;
+constexpr int kTileCols = 12;
 constexpr int kTileSlots = kTileRows * kTileCols;
 constexpr int kTileBytes = kTileSlots * 10;  // rho f32 | grad half2 | template f16
 constexpr int kTileWords = kTileBytes / 4;
-static_assert(kTileSlots == VORS_STAGE_CHUNKS * 64, "a tile is one ring stage of the align kernel");
+static_assert(kTileCols % 4 == 0 && kTileCols % 3 == 0, "quads of words per 16-byte load; three-deep software pipeline");
 
 struct Geom {
     int L;
@@ -84,10 +85,10 @@ struct Geom {
     int per_row, per_page;       // cells per atlas row / per atlas page
 };
 
-// word offsets of slot (j, lane) of a tile inside its 640-word stage
+// word offsets of slot (j, lane) of a tile inside its kTileWords-word stage
 __host__ __device__ __forceinline__ int tile_rho_word(int j, int lane) { return (j >> 2) * 128 + lane * 4 + (j & 3); }
-__host__ __device__ __forceinline__ int tile_grad_word(int j, int lane) { return 256 + tile_rho_word(j, lane); }
-__host__ __device__ __forceinline__ int tile_tmpl_half(int j, int lane) { return 1024 + lane * 8 + j; }  // index in halves
+__host__ __device__ __forceinline__ int tile_grad_word(int j, int lane) { return kTileSlots + tile_rho_word(j, lane); }
+__host__ __device__ __forceinline__ int tile_tmpl_half(int j, int lane) { return 4 * kTileSlots + tile_rho_word(j, lane); }  // index in halves
 
 // ---- candidate record fields -----------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint32_t rec_pack_pk(int x, int y, uint32_t tmpl) { return uint32_t(x) | (uint32_t(y) << 12) | (tmpl << 24); }
