@@ -437,11 +437,17 @@ def parity_in_run(cfg, gray_h, depth_h, kw, n_streams, T, fi, poses_log):
 
     def worst(a, b):
         mr = mm = 0.0
+        at = None
+        per_step = []
         for k in range(1, T + 1):
+            sm = 0.0
             for s in range(n_streams):
                 r, m = O.pose_error(a[k, s], b[k, s])
-                mr, mm = max(mr, r), max(mm, m)
-        return {"max_rad": mr, "max_m": mm}
+                if m > mm:
+                    at = {"step": k, "stream": s, "frame": fi(k)}
+                mr, mm, sm = max(mr, r), max(mm, m), max(sm, m)
+            per_step.append(float("%.2g" % sm))
+        return {"max_rad": mr, "max_m": mm, "worst_at": at, "max_m_per_step": per_step}
 
     against = {m: {arm: worst(gp, oracle_poses[m]) for arm, gp in poses_log.items()} for m in modes}
     decides = "f64" if dense else "f32_sequential"

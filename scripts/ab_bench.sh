@@ -10,7 +10,9 @@ for v in /tmp/stock.so visual-odometry-rs_b200/lib_variants/*.so; do
   name=$(basename $v .so)
   extra=""
   if [[ "$name" =~ _n([0-9]+)$ ]]; then extra="--streams ${BASH_REMATCH[1]}"; fi
-  python bench.py --no-cpu-baseline --steps 6 --warmup 3 $extra ${AB_ARGS} > /tmp/ab.json 2> /tmp/ab.err; rc=$?
+  envs=""
+  if [[ "$name" =~ _generic$ ]]; then envs="VORS_NO_TILED=1"; fi  # dense keyframes through the generic (compacted) records
+  env $envs python bench.py --no-cpu-baseline --steps ${AB_STEPS:-6} --warmup ${AB_WARMUP:-3} $extra ${AB_ARGS} > /tmp/ab.json 2> /tmp/ab.err; rc=$?
   [ -s /tmp/ab.json ] || { echo "$name: FAILED rc=$rc"; tail -3 /tmp/ab.err; continue; }
   python -c "
 import json,sys; d=json.load(open('/tmp/ab.json')); r=d['roofline']; p=d.get('parity_in_run',{})

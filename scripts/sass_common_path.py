@@ -37,15 +37,17 @@ def main():
             ins.append((int(m.group(1), 16), m.group(2).strip()))
     at = {a: i for i, (a, _) in enumerate(ins)}
     bra = re.compile(r"BRA(?:\.U)?(?:\.DIV)?\s+((?:!?U?P\d|UR\d+),\s*)?0x([0-9a-f]+)")
-    loops = []
+    loops, inner = [], []
     for a, x in ins:
         m = bra.search(x)
         if m and int(m.group(2), 16) < a:
             t = int(m.group(2), 16)
             body = [y for (b, y) in ins if t <= b <= a]
             gathers = sum("LDG.E.U8" in y for y in body), sum("TLD4" in y for y in body)
-            if gathers in ((32, 0), (0, 8), (0, 12)) and any("UBLKCP" in y for y in body):  # byte loads, or -DVORS_TEX=1: one gather each
+            if gathers in ((32, 0), (0, 8), (0, 12), (0, 6)) and any("UBLKCP" in y for y in body):  # byte loads, or -DVORS_TEX=1: one gather each
                 loops.append((a - t, t, a))
+            if gathers == (0, 6) and not any("UBLKCP" in y for y in body):
+                inner.append((a - t, t, a))
     _, head, tail = min(loops)
     start, end = at[head], at[tail]
     dist, prev, pq = {start: 0}, {}, [(0, start)]
@@ -78,6 +80,12 @@ def main():
         p = ins[i][1].split()
         ops[(p[1] if p[0].startswith("@") else p[0]).split(".")[0]] += 1
     n_words = max(8, sum("TLD4" in ins[i][1] for i in path))  # words (= candidates per lane) per iteration: 8, or 12 tiled
+    if inner:  # tiled records: the unrolled half tile (six words) is an inner loop that runs twice per stage
+        _, ih, it = min(inner)
+        n_in = sum(1 for i in path if ih <= ins[i][0] <= it)
+        print(f"inner half-tile loop {ih:#x}..{it:#x}: {(it - ih) // 16 + 1} instructions in the body, {n_in} on the common path = "
+              f"{n_in / 6:.3f} per candidate; per stage of 12: {len(path) + n_in} = {(len(path) + n_in) / 12:.3f} per candidate")
+        n_words = 6
     print(f"loop {head:#x}..{tail:#x}: {(tail - head) // 16 + 1} instructions in the body, common path {len(path)} "
           f"= {len(path) / n_words:.3f} per candidate ({n_words} per iteration); BRA.DIV on it: {sum('BRA.DIV' in ins[i][1] for i in path)}")
     print(sorted(ops.items(), key=lambda kv: -kv[1]))

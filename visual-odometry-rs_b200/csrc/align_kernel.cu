@@ -74,6 +74,7 @@ constexpr int kRingWords = kStageWords > kTileWords ? kStageWords : kTileWords; 
 constexpr uint32_t kRingBytes = kRingWords * 4;
 constexpr int kTileWordsBm = kTileSlots / 32;  // bitmap words per tile
 constexpr int kHsmStride = 21;  // odd: scalar accesses of a warp hit 32 distinct banks
+constexpr int kStashCap = 16;   // boundary-band candidates a warp stashes per pass (beyond that: bitmap scan)
 static_assert(kStageCand == kPtAlign, "levels are padded to whole ring stages");
 
 struct LmShared {
@@ -95,7 +96,6 @@ struct LmShared {
     unsigned long long point_passes;
     float warp_part[kWarps][32];   // per-warp sums of the pass accumulators (E, n, 9 moments / g[6] / Huber: g[6] and H[21])
     double hout[kWarps][21];       // per-warp sum of J J^T over the candidates outside for sure, cumulative over a level's passes
-    double hout_pass[kWarps][21];  // per-warp sum of J J^T over this pass's deferred candidates that turned out outside
     double h_total[21];            // the level's H_total (k_h_total), cached for the per-pass serial part
     double raw[kNumRaw];           // CTA / team totals of the raw accumulators
     double tot[32];                // finished pass: sum r^2, n_inside, g[6], H[21]
@@ -104,7 +104,9 @@ struct LmShared {
     long long dbgw[8][4];
     long long dbgs[8][4];
 #endif
-    uint32_t near_words[kWarps][2 * 32];  // (word, mask) pairs flagged for deferred_pass by each warp in this pass
+    // boundary-band candidates flagged by each warp in this pass, stashed with what their exact re-evaluation needs
+    // (slot, a = x - cx, b = y - cy, inverse depth, gradient bits, template value): no record is read twice
+    uint32_t stash[kWarps][kStashCap][6];
     alignas(8) unsigned long long full_bar[kWarps][kStages];
     alignas(128) float ring[kWarps][kStages * kRingWords];
     // per-thread J J^T accumulators of the hot loop (candidates that changed sides of the frame border): 21 floats at an
@@ -154,6 +156,11 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return fmaf(r, fmaf(-x, r, 1.0f), r);
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -322,11 +329,11 @@ __shared__ LevelConst s_lc;
 // After the hot loop each warp revisits the flagged slots of its own stages: the reference's own arithmetic
 // (lm_optimizer.rs:213-231) decides membership; inside candidates are evaluated in full, outside ones contribute
 // J J^T to H_outside.  Keeping all of this (and its function calls) out of the hot loop keeps that loop call-free.
-constexpr int kNearWords = 32;  // flagged bitmap words a warp remembers per pass (beyond that: full bitmap scan)
 
 // Fields of candidate slot `i` of a level, from its record in global memory (deferred pass, optical flow).
 struct SlotRec {
     float x, y, rho, gu, gv, tmpl;
+    uint32_t gr;
 };
 template <bool kTiled>
 __device__ __forceinline__ SlotRec load_slot(const uint32_t* __restrict__ pts, int tiles_y, int i) {
@@ -339,6 +346,7 @@ __device__ __forceinline__ SlotRec load_slot(const uint32_t* __restrict__ pts, i
         r.y = float(kTileRows * ty + ln);
         r.rho = __uint_as_float(__ldg(w + tile_rho_word(j, ln)));
         const uint32_t gr = __ldg(w + tile_grad_word(j, ln));
+        r.gr = gr;
         r.gu = rec_gx(gr);
         r.gv = rec_gy(gr);
         r.tmpl = __half2float(__ushort_as_half(__ldg(reinterpret_cast<const unsigned short*>(w) + tile_tmpl_half(j, ln))));
@@ -347,6 +355,7 @@ __device__ __forceinline__ SlotRec load_slot(const uint32_t* __restrict__ pts, i
         r.rho = __uint_as_float(__ldg(pts + pt_word(i, 1)));
         r.x = float(rec_x(pk));
         r.y = float(rec_y(pk));
+        r.gr = gr;
         r.gu = rec_gx(gr);
         r.gv = rec_gy(gr);
         r.tmpl = float(rec_tmpl(pk));
@@ -354,18 +363,23 @@ __device__ __forceinline__ SlotRec load_slot(const uint32_t* __restrict__ pts, i
     return r;
 }
 
-// One deferred candidate: the reference's own warp decides (lm_optimizer.rs:213-231); inside -> full evaluation into
-// `acc`, outside -> J J^T into h.
-template <bool kSkew, bool kHuber, bool kTiled>
-__device__ __forceinline__ void eval_deferred(int i, const LevelConst& lc, const Pose& model, Acc<kHuber>& acc, int& fixed, float (&h)[21]) {
+template <bool kSkew>
+__device__ __forceinline__ void add_outside(float sign, uint32_t gr, float a, float b, float rho, const Intrinsics& k, float* hs);
+
+// One deferred candidate: the reference's own warp decides (lm_optimizer.rs:213-231).  Inside -> full evaluation into `acc`.
+// Outside -> it joins the candidates that are outside for sure: its bit is set in the level's far bitmap and its J J^T goes
+// to the thread's shared-memory accumulators like any other candidate that changed sides (H = H_total - H_outside); the
+// next pass takes it out again if it is no longer outside.
+template <bool kSkew, bool kHuber>
+__device__ __forceinline__ void eval_deferred(int slot, float ca, float cb, float rho, uint32_t gr, float tmpl, const LevelConst& lc,
+                                              const Pose& model, Acc<kHuber>& acc, int& fixed, uint32_t* far_bitmap, float* hs, int& any_flip) {
     const Intrinsics k = lc.k;
     const int rows = int(lc.rows);
-    const SlotRec sr = load_slot<kTiled>(lc.pts, lc.tiles_y, i);
-    const float rho = sr.rho, x = sr.x, y = sr.y, gu = sr.gu, gv = sr.gv;
-    const float2 uv = warp_exact(model, k, x, y, rho);
+    const float gu = rec_gx(gr), gv = rec_gy(gr);
+    // x, y are integers and a = fl(x - cx) is at most 2^-17 away from x - cx: rounding a + cx to the nearest integer restores them
+    const float2 uv = warp_exact(model, k, rintf(ca + lc.cx), rintf(cb + lc.cy), rho);
     // 0 <= floor(u) < W-2  <=>  0 <= u < W-2 (W-2 is an integer); NaN compares false -> outside
     const bool inside = (uv.x >= 0.0f) && (uv.x < lc.wm2) && (uv.y >= 0.0f) && (uv.y < lc.hm2);
-    const float ca = x - lc.cx, cb = y - lc.cy;
     if (inside) {
         const float fu = floorf(uv.x), fv = floorf(uv.y);
         const float a = uv.x - fu, b = uv.y - fv;
@@ -373,7 +387,7 @@ __device__ __forceinline__ void eval_deferred(int i, const LevelConst& lc, const
         const float t00 = float(__ldg(p)), t10 = float(__ldg(p + 1)), t01 = float(__ldg(p + rows)), t11 = float(__ldg(p + rows + 1));
         const float top = fmaf(a, t01 - t00, t00), bot = fmaf(a, t11 - t10, t10);
         const float val = fmaf(b, bot - top, top);  // same lerp form as `back`
-        const float r = val - sr.tmpl;
+        const float r = val - tmpl;
         ++fixed;
         if constexpr (kHuber) {
             float J[6];
@@ -391,93 +405,82 @@ __device__ __forceinline__ void eval_deferred(int i, const LevelConst& lc, const
             }
         }
     } else if (!kHuber) {
-        float J[6];
-        jacobian_centred<kSkew>(gu, gv, ca, cb, rho, k, J);
-#pragma unroll
-        for (int q = 0; q < 6; ++q)
-#pragma unroll
-            for (int d = q; d < 6; ++d) h[tri(q, d)] = fmaf(J[q], J[d], h[tri(q, d)]);
+        atomicOr(far_bitmap + (slot >> 5), 1u << (slot & 31));
+        add_outside<kSkew>(1.0f, gr, ca, cb, rho, k, hs);
+        any_flip = 1;
     }
 }
 
-// `wlist`: the (word, mask) pairs this warp flagged in the hot loop (n_words of them, only the first kNearWords stored);
-// `scratch`: this warp's ring memory (idle between passes), used as the compacted candidate list.
+// The boundary-band candidates of this warp's stages, after its hot loop.  Common case: they were stashed (at most kStashCap
+// of them): one per lane, side by side.  Otherwise (e.g. a static camera: the x = 0 column and the y = 0 row sit exactly on
+// the inside-test boundary) this warp's part of the near bitmap is scanned and the records are read back.
+// `scratch`: this warp's ring memory (idle between passes), used as the compacted candidate list of the scan.
+// `small_words` > 0: the level went through the small-level path (its `small_words` bitmap words dealt round-robin to the warps).
 template <bool kSkew, bool kHuber, bool kTiled>
-__device__ __noinline__ void deferred_pass(int warp, int lane, int first_stage, int stage_stride, int n_stages, uint32_t* __restrict__ bitmap,
-                                           const uint32_t* wlist, int n_words, uint32_t* scratch, Acc<kHuber>* acc_io, int* n_fix) {
+__device__ __noinline__ void deferred_pass(int warp, int lane, int first_stage, int stage_stride, int n_stages, int small_words,
+                                           uint32_t* __restrict__ bitmap, uint32_t* __restrict__ far_bitmap, int n_near, uint32_t* scratch,
+                                           float* hs, Acc<kHuber>* acc_io, int* n_fix, int* any_flip_io) {
     LmShared& S = lm_shared();
     const LevelConst& lc = s_lc;
     Acc<kHuber> acc = *acc_io;
-    int fixed = 0;
-    float h[21];
-#pragma unroll
-    for (int c = 0; c < 21; ++c) h[c] = 0.0f;
-    // One round: every lane brings one flagged bitmap word (`mask` over the 32 slots starting at slot `base`); the set bits of
-    // the whole warp are compacted into `scratch` (at most 1024 entries) and evaluated one candidate per lane and step.
-    auto round = [&](uint32_t mask, int base) {
-        if (!kTiled && base + 32 > lc.n) mask = base >= lc.n ? 0u : (mask & ((1u << (lc.n - base)) - 1u));  // padding slots
-        const int cnt = __popc(mask);
-        int incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
+    int fixed = 0, any_flip = 0;
+    if (n_near <= kStashCap) {
+        if (lane < n_near) {
+            const uint32_t* e = S.stash[warp][lane];
+            const int slot = int(e[0]);
+            bitmap[slot >> 5] = 0u;  // leave the near bitmap all-zero for the next pass
+            eval_deferred<kSkew, kHuber>(slot, __uint_as_float(e[1]), __uint_as_float(e[2]), __uint_as_float(e[3]), e[4], __uint_as_float(e[5]), lc,
+                                         S.cand_model, acc, fixed, far_bitmap, hs, any_flip);
         }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        int off = incl - cnt;
-        while (mask) {
-            scratch[off++] = uint32_t(base) + uint32_t(__ffs(mask) - 1);
-            mask &= mask - 1u;
-        }
-        __syncwarp();
-        for (int e = lane; e < total; e += 32) eval_deferred<kSkew, kHuber, kTiled>(int(scratch[e]), lc, S.cand_model, acc, fixed, h);
-        __syncwarp();
-    };
-    if (n_words <= kNearWords) {
-        // common case: the flagged words were remembered
-        uint32_t word = 0u, mask = 0u;
-        if (lane < n_words) {
-            word = wlist[2 * lane];
-            mask = wlist[2 * lane + 1];
-            bitmap[word] = 0u;  // leave the bitmap all-zero for the next pass
-        }
-        round(mask, int(word) * 32);
     } else {
-        // more flagged words than remembered (e.g. a static camera: the x = 0 column and the y = 0 row sit exactly on the
-        // inside-test boundary): scan this warp's part of the bitmap, one group of 128 slots (a uint4 of bitmap words) per lane
-        constexpr int kGroups = (kTiled ? kTileSlots : kStageCand) / 128;
-        const int my_groups = first_stage < n_stages ? ((n_stages - first_stage + stage_stride - 1) / stage_stride) * kGroups : 0;
-        for (int g0 = 0; g0 < my_groups; g0 += 32) {  // warp-uniform trip count
-            const int gi = g0 + lane;
-            int grp = 0;
-            uint4 w4 = make_uint4(0u, 0u, 0u, 0u);
-            if (gi < my_groups) {
-                grp = (first_stage + (gi / kGroups) * stage_stride) * kGroups + gi % kGroups;  // 128-slot group index in the level
-                uint4* wp = reinterpret_cast<uint4*>(bitmap) + grp;
-                w4 = *wp;
-                if (w4.x | w4.y | w4.z | w4.w) *wp = make_uint4(0u, 0u, 0u, 0u);
+        // One round: every lane brings one flagged bitmap word (`mask` over the 32 slots starting at slot `base`); the set bits of
+        // the whole warp are compacted into `scratch` (at most 1024 entries) and evaluated one candidate per lane and step.
+        auto round = [&](uint32_t mask, int base) {
+            const int cnt = __popc(mask);
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
             }
-            if (!__any_sync(0xffffffffu, (w4.x | w4.y | w4.z | w4.w) != 0u)) continue;
-            round(w4.x, grp * 128);
-            round(w4.y, grp * 128 + 32);
-            round(w4.z, grp * 128 + 64);
-            round(w4.w, grp * 128 + 96);
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            int off = incl - cnt;
+            while (mask) {
+                scratch[off++] = uint32_t(base) + uint32_t(__ffs(mask) - 1);
+                mask &= mask - 1u;
+            }
+            __syncwarp();
+            for (int e = lane; e < total; e += 32) {
+                const int slot = int(scratch[e]);
+                const SlotRec sr = load_slot<kTiled>(lc.pts, lc.tiles_y, slot);
+                eval_deferred<kSkew, kHuber>(slot, sr.x - lc.cx, sr.y - lc.cy, sr.rho, sr.gr, sr.tmpl, lc, S.cand_model, acc, fixed, far_bitmap, hs,
+                                             any_flip);
+            }
+            __syncwarp();
+        };
+        // this warp's bitmap words, one per lane and round: the words of its stages, or its share of a small level's words
+        constexpr int kW = kTiled ? kTileWordsBm : kStageWordsBm;
+        const int my_words = small_words > 0 ? (small_words > first_stage ? (small_words - first_stage + stage_stride - 1) / stage_stride : 0)
+                                             : (first_stage < n_stages ? ((n_stages - first_stage + stage_stride - 1) / stage_stride) * kW : 0);
+        for (int k0 = 0; k0 < my_words; k0 += 32) {  // warp-uniform trip count
+            const int kk = k0 + lane;
+            int word = 0;
+            uint32_t mask = 0u;
+            if (kk < my_words) {
+                word = small_words > 0 ? first_stage + kk * stage_stride : (first_stage + (kk / kW) * stage_stride) * kW + kk % kW;
+                mask = bitmap[word];
+                if (mask) bitmap[word] = 0u;  // leave the near bitmap all-zero for the next pass
+            }
+            if (!__any_sync(0xffffffffu, mask != 0u)) continue;
+            round(mask, word * 32);
         }
+        // `scratch` is ring memory: order these generic-proxy accesses before the next pass's bulk copies (async proxy)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncwarp();
-    if (!kHuber) {
-#pragma unroll
-        for (int c = 0; c < 21; ++c) {
-            float v = h[c];
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-            if (lane == 0) S.hout_pass[warp][c] += double(v);
-        }
-    }
     *acc_io = acc;
     *n_fix = fixed;
-    // `scratch` is ring memory: order these generic-proxy accesses before the next pass's bulk copies (async proxy)
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    *any_flip_io |= __any_sync(0xffffffffu, any_flip != 0) ? 1 : 0;
 }
 
 // Per-level constants the common path keeps in registers.
@@ -490,19 +493,20 @@ struct PassConst {
 };
 
 // floor / fraction of a warped coordinate and the texel fetch of its 2x2 footprint (common tail of every front).
-__device__ __forceinline__ void sample_front(float u, float v, const PassConst& lc, Front& f) {
+// (`ku`, `kv`: the texture offsets lc.tex_ku / lc.tex_kv, or a lane's own copies of them: see TileLane)
+__device__ __forceinline__ void sample_front(float u, float v, const PassConst& lc, Front& f, float ku, float kv) {
 #if VORS_TEX
 #if VORS_FRND
     const float fu = floorf(u), fv = floorf(v);
     f.fa = u - fu;
     f.fb = v - fv;
-    tex_gather(lc.tex, fv + (8388608.0f - lc.tex_kv), fu + (8388608.0f - lc.tex_ku), f.t00, f.t10, f.t01, f.t11);
+    tex_gather(lc.tex, fv + (8388608.0f - kv), fu + (8388608.0f - ku), f.t00, f.t10, f.t01, f.t11);
 #else
     // tu = 2^23 + floor(u) exactly (round-down add; 0 <= u < 2^22 on this path)
     const float tu = __fadd_rd(u, 8388608.0f), tv = __fadd_rd(v, 8388608.0f);
     f.fa = u - (tu - 8388608.0f);
     f.fb = v - (tv - 8388608.0f);
-    tex_gather(lc.tex, tv - lc.tex_kv, tu - lc.tex_ku, f.t00, f.t10, f.t01, f.t11);
+    tex_gather(lc.tex, tv - kv, tu - ku, f.t00, f.t10, f.t01, f.t11);
 #endif
 #else
     // floor and fraction without F2I / I2F (see kMagicBits)
@@ -516,6 +520,7 @@ __device__ __forceinline__ void sample_front(float u, float v, const PassConst& 
     f.t11 = __ldg(p + lc.rows + 1);
 #endif
 }
+__device__ __forceinline__ void sample_front(float u, float v, const PassConst& lc, Front& f) { sample_front(u, v, lc, f, lc.tex_ku, lc.tex_kv); }
 
 // bilinear sample in lerp form minus the template value: the same interpolant as lm_optimizer.rs:241-246 (a along x, b along
 // y) with 6 instead of 10 operations; it differs from the reference's four-product expression by ~1 ulp of the value, far
@@ -541,8 +546,7 @@ struct Defer {
     uint32_t* far;     // this level's bitmap of the slots that were outside for sure in the previous pass of the level
     int n_bad;         // slots of this pass redirected to the zero page so far
     int n_near;        // of which flagged in `near`
-    int n_words;       // bitmap words flagged in `near` during this pass
-    uint32_t* wlist;   // (word, mask) of the first kNearWords of them (shared memory)
+    uint32_t* stash;   // this warp's stash of the flagged candidates (shared memory, kStashCap entries of 6 words)
     int any_flip;      // this warp added to its hsm accumulators during this pass
     int first_pass;    // first pass of the level: the far bitmap holds nothing yet
 };
@@ -597,7 +601,7 @@ __device__ __forceinline__ FrontA front_a(uint32_t pk, float rho, uint32_t gr, c
 // The rare, warp-uniform part of a front: bookkeeping of the slots of this 32-slot word that the common path cannot evaluate.
 // `not_ok`: ballot of the lanes not inside for sure; `old_far`: the word's far-bitmap word from the previous pass of the level.
 template <bool kSkew, bool kHuber>
-__device__ __forceinline__ void rare_slots(unsigned not_ok, float u, float v, float rho, uint32_t gr, float a, float b, int word,
+__device__ __forceinline__ void rare_slots(unsigned not_ok, float u, float v, float rho, uint32_t gr, float tmpl, float a, float b, int word,
                                            unsigned old_far, const PassConst& lc, const Intrinsics& k, Defer& df, float* hs, int lane) {
     // H over the inside set = H_total - H_outside (lm_optimizer.rs:100 sums J J^T over the inside set).  H_outside is
     // maintained incrementally across the passes of a level: only candidates that were outside for sure in the previous
@@ -612,17 +616,20 @@ __device__ __forceinline__ void rare_slots(unsigned not_ok, float u, float v, fl
         add_outside<kSkew>(sign, gr, a, b, rho, k, hs);
         df.any_flip = 1;
     }
-    if (lane == 0) {
-        if (flips) df.far[word] = far_mask;
-        if (near_mask) {  // boundary band / NaN coordinates of a live candidate: see deferred_pass
-            df.near[word] = near_mask;
-            if (df.n_words < kNearWords) {
-                df.wlist[2 * df.n_words] = uint32_t(word);
-                df.wlist[2 * df.n_words + 1] = near_mask;
-            }
+    if (lane == 0 && flips) df.far[word] = far_mask;
+    if (near_mask) {  // boundary band / NaN coordinates of a live candidate: see deferred_pass
+        if (lane == 0) df.near[word] = near_mask;
+        const int at = df.n_near + __popc(near_mask & ((1u << lane) - 1u));
+        if (((near_mask >> lane) & 1u) && at < kStashCap) {
+            uint32_t* e = df.stash + 6 * at;
+            e[0] = uint32_t(word) * 32u + uint32_t(lane);
+            e[1] = __float_as_uint(a);
+            e[2] = __float_as_uint(b);
+            e[3] = __float_as_uint(rho);
+            e[4] = gr;
+            e[5] = __float_as_uint(tmpl);
         }
     }
-    df.n_words += near_mask ? 1 : 0;
     df.n_bad += __popc(not_ok);
     df.n_near += __popc(near_mask);
 }
@@ -640,7 +647,7 @@ __device__ __forceinline__ void front_b(const FrontA& x, int word, int j, unsign
     const unsigned not_ok = __ballot_sync(0xffffffffu, !ok);
     if (not_ok | (old_nz & (1u << j))) {  // warp-uniform, rare
         const unsigned old_far = __shfl_sync(0xffffffffu, old_words, j);
-        rare_slots<kSkew, kHuber>(not_ok, u, v, rho, gr, x.a, x.b, word, old_far, lc, k, df, hs, lane);
+        rare_slots<kSkew, kHuber>(not_ok, u, v, rho, gr, u2f(pk >> 24), x.a, x.b, word, old_far, lc, k, df, hs, lane);
         if (!ok) {
             u = lc.zero_u;
             v = lc.zero_v;
@@ -661,14 +668,23 @@ __device__ __forceinline__ void front_b(const FrontA& x, int word, int j, unsign
 // Per-lane constants of one tile (= ring stage): the lane's row, and the part of the folded warp that does not depend on the
 // word (column) or on the inverse depth: [Ub Vb Wb] = M[:, 0] a0 + M[:, 1] b + M[:, 2] with a0 = x0 - cx of the tile's first
 // column and b = y - cy of the lane's row.  Word j then costs two FFMAs per row of the matrix: M[:, 0] j + . and M[:, 3] rho + .
+// Rows of a tile below the image (levels whose height is not a multiple of 32) are DEAD lanes: their records hold a zero
+// inverse depth, gradient and template, and they get constants of their own - [Ub Vb Wb] = 2^20 [u* - cx, v* - cy, 1] with
+// (u*, v*) the middle of the image, so that they pass the inside test in every word whatever the model (the word-dependent
+// terms are 2^-20 of that), and texture offsets (ku, kv) that send their gather to the zero page: residual 0 - 0, zero
+// gradient, no trip through the rare path.  They are subtracted from the slot count instead.
 struct TileLane {
     float a0, b, Ub, Vb, Wb;
     float M0v, M4v, M8v;
+    float ku, kv;
 };
 // front of word j of a tile (tiled records only exist for zero skew, plain L2: see AlignParams::tiled).
 // `tmpl`: the slot's template value; travels in Front::pk as f32 bits.
+// J: the word within its half tile (compile time); `t` holds the half tile's constants (a0, Ub, Vb, Wb of its first column),
+// `word` its first bitmap word, `jh` its first word within the tile, `old_nz` the tile's non-zero far words shifted so
+// that bit J is this word's.
 template <int J>
-__device__ __forceinline__ void tile_front(const TileLane& t, float rho, uint32_t gr, float tmpl, const float (&M)[12], int word,
+__device__ __forceinline__ void tile_front(const TileLane& t, float rho, uint32_t gr, float tmpl, const float (&M)[12], int word, int jh,
                                            unsigned old_words, unsigned old_nz, const PassConst& lc, const Intrinsics& k, Defer& df,
                                            float* hs, int lane, Front& f) {
     // (M0v, M4v, M8v: the first matrix column in ordinary registers - an FFMA takes one uniform-register or immediate operand,
@@ -683,8 +699,8 @@ __device__ __forceinline__ void tile_front(const TileLane& t, float rho, uint32_
     const bool ok = (fabsf(u - lc.hu) < lc.lo_u) & (fabsf(v - lc.hv) < lc.lo_v);
     const unsigned not_ok = __ballot_sync(0xffffffffu, !ok);
     if (not_ok | (old_nz & (1u << J))) {  // warp-uniform, rare
-        const unsigned old_far = __shfl_sync(0xffffffffu, old_words, J);
-        rare_slots<false, false>(not_ok, u, v, rho, gr, a, t.b, word, old_far, lc, k, df, hs, lane);
+        const unsigned old_far = __shfl_sync(0xffffffffu, old_words, jh + J);
+        rare_slots<false, false>(not_ok, u, v, rho, gr, tmpl, a, t.b, word + J, old_far, lc, k, df, hs, lane);
         if (!ok) {
             u = lc.zero_u;
             v = lc.zero_v;
@@ -693,7 +709,7 @@ __device__ __forceinline__ void tile_front(const TileLane& t, float rho, uint32_
             gr = 0u;
         }
     }
-    sample_front(u, v, lc, f);
+    sample_front(u, v, lc, f, t.ku, t.kv);
     f.pk = __float_as_uint(tmpl);
     f.gr = gr;
     f.a = a;
@@ -876,7 +892,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
             for (int st = 0; st < kStages; ++st) mbar_init(smem_u32(&S.full_bar[w][st]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < kWarps * 21) (&S.hout[0][0])[tid] = (&S.hout_pass[0][0])[tid] = 0.0;
+    if (tid < kWarps * 21) (&S.hout[0][0])[tid] = 0.0;
 #if VORS_TIMING
     if (tid < 96) (&S.dbg[0][0])[tid] = 0;
 #endif
@@ -886,6 +902,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
     for (int job_idx = team_id; job_idx < P.n_jobs; job_idx += n_teams) {
         const AlignJob& job = P.jobs[job_idx];
         const bool writer = (rank == 0);
+        if (writer && tid == 0) P.results[job_idx].t_begin_ns = global_timer_ns();
         if (tid == 0) {
             S.out_model = P.init[job_idx];
             S.failed = 0;
@@ -971,8 +988,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                     df.far = lj.defer_far;
                     df.n_bad = 0;
                     df.n_near = 0;
-                    df.n_words = 0;
-                    df.wlist = S.near_words[warp];
+                    df.stash = &S.stash[warp][0][0];
                     df.any_flip = 0;
                     df.first_pass = __shfl_sync(0xffffffffu, S.init_phase, 0);
                     float* hs = S.hsm[tid];
@@ -1015,6 +1031,11 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                         int tx = gw / tiles_y, ty = gw - tx * tiles_y;
                         const int dtx = TW / tiles_y, dty = TW - dtx * tiles_y;
                         const float lane_f = float(lane);
+                        const int rows_lvl = int(s_lc.rows);
+                        // dead lanes (see TileLane): the middle of the inside range, and texture offsets that turn it into the zero page
+                        const float mid_u = floorf(lc.hu), mid_v = floorf(lc.hv);
+                        const float dead_U = ((mid_u + 0.5f) - lc.cx) * 1048576.0f, dead_V = ((mid_v + 0.5f) - lc.cy) * 1048576.0f;
+                        const float dead_ku = lc.tex_ku + (mid_u - lc.zero_u), dead_kv = lc.tex_kv + (mid_v - lc.zero_v);
                         TileLane tl;
                         // thread-dependent on paper (threadIdx.y is 0 in every thread of this 1-D block, which the compiler cannot
                         // know), so that these values live in ordinary registers instead of uniform ones
@@ -1036,41 +1057,57 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                             tl.Ub = fmaf(M[1], tl.b, fmaf(tl.M0v, tl.a0, M[2]));
                             tl.Vb = fmaf(M[5], tl.b, fmaf(tl.M4v, tl.a0, M[6]));
                             tl.Wb = fmaf(M[9], tl.b, fmaf(tl.M8v, tl.a0, M[10]));
+                            tl.ku = lc.tex_ku;
+                            tl.kv = lc.tex_kv;
+                            const int rows_live = min(kTileRows, rows_lvl - kTileRows * ty);  // rows of this tile inside the image
+                            if (lane >= rows_live) {  // dead lanes (see TileLane)
+                                tl.Ub = dead_U;
+                                tl.Vb = dead_V;
+                                tl.Wb = 1048576.0f;
+                                tl.ku = dead_ku;
+                                tl.kv = dead_kv;
+                            }
                             mbar_wait(bar_base + ring_slot * 8u, ring_parity);  // TMA bytes have landed
                             const unsigned old_words = old_next;
                             const unsigned old_nz = __ballot_sync(0xffffffffu, old_words != 0u);
                             far_ptr += far_step;
                             if (far_lane && c + TW < n_stages) old_next = __ldcg(far_ptr);
                             const float* sp = &S.ring[warp][ring_slot * kRingWords];
-                            const float4* r4 = reinterpret_cast<const float4*>(sp) + lane;                    // inverse depths, 4 words each
-                            const uint4* g4 = reinterpret_cast<const uint4*>(sp + kTileSlots) + lane;          // gradients (half2)
-                            const uint2* t2 = reinterpret_cast<const uint2*>(sp + 2 * kTileSlots) + lane;      // template values (f16 x 4)
-                            const int w0 = kTileWordsBm * c;
                             // software pipeline, three slots: word J's front (its texture gather) is issued two words before its
-                            // back, so two gathers per lane are in flight while a third word is being reduced
+                            // back, so two gathers per lane are in flight while a third word is being reduced.  The body is
+                            // unrolled over half a tile (six words = two rounds of the three slots) and run twice: twelve words
+                            // unrolled do not fit the instruction cache.
 #define VORS_TSTEP(J, RHO, GR, TMPL, FNEW, FOLD)                                                                            \
-    tile_front<J>(tl, RHO, GR, TMPL, M, w0 + (J), old_words, old_nz, lc, k, df, hs, lane, FNEW);                            \
+    tile_front<J>(tl, RHO, GR, TMPL, M, w0, jh, old_words, old_nz_h, lc, k, df, hs, lane, FNEW);                            \
     tile_back(FOLD, acc);
-#define VORS_TQUAD(H, FA, FB, FC)                                                                                           \
-    {                                                                                                                       \
-        const float4 rq = r4[32 * (H)];                                                                                     \
-        const uint4 gq = g4[32 * (H)];                                                                                      \
-        const uint2 tq = t2[32 * (H)];                                                                                      \
-        VORS_TSTEP(4 * (H) + 0, rq.x, gq.x, half_lo(tq.x), FA, FB)                                                          \
-        VORS_TSTEP(4 * (H) + 1, rq.y, gq.y, half_hi(tq.x), FB, FC)                                                          \
-        VORS_TSTEP(4 * (H) + 2, rq.z, gq.z, half_lo(tq.y), FC, FA)                                                          \
-        VORS_TSTEP(4 * (H) + 3, rq.w, gq.w, half_hi(tq.y), FA, FB)                                                          \
-    }
-                            // word J fills slot J % 3 and consumes slot (J + 1) % 3 = word J - 2
-                            VORS_TQUAD(0, f0, f1, f2)
-                            VORS_TQUAD(1, f1, f2, f0)
-                            VORS_TQUAD(2, f2, f0, f1)
-#undef VORS_TQUAD
+#pragma unroll 1
+                            for (int h = 0; h < 2; ++h) {
+                                const int jh = kTileHalfCols * h, w0 = kTileWordsBm * c + jh;
+                                const unsigned old_nz_h = old_nz >> jh;
+                                // the lane's six inverse depths, gradients and template values of this half tile
+                                const float2* r2 = reinterpret_cast<const float2*>(sp + (h * kTileRows + lane) * kTileHalfCols);
+                                const uint2* g2 = reinterpret_cast<const uint2*>(sp + kTileSlots + (h * kTileRows + lane) * kTileHalfCols);
+                                const uint32_t* t1 = reinterpret_cast<const uint32_t*>(sp + 2 * kTileSlots) + (h * kTileRows + lane) * (kTileHalfCols / 2);
+                                const float2 ra = r2[0], rb = r2[1], rc = r2[2];
+                                const uint2 ga = g2[0], gb = g2[1], gc = g2[2];
+                                const uint32_t ta = t1[0], tb = t1[1], tc = t1[2];
+                                VORS_TSTEP(0, ra.x, ga.x, half_lo(ta), f0, f1)
+                                VORS_TSTEP(1, ra.y, ga.y, half_hi(ta), f1, f2)
+                                VORS_TSTEP(2, rb.x, gb.x, half_lo(tb), f2, f0)
+                                VORS_TSTEP(3, rb.y, gb.y, half_hi(tb), f0, f1)
+                                VORS_TSTEP(4, rc.x, gc.x, half_lo(tc), f1, f2)
+                                VORS_TSTEP(5, rc.y, gc.y, half_hi(tc), f2, f0)
+                                // the second half starts six columns further
+                                tl.a0 += float(kTileHalfCols);
+                                tl.Ub = fmaf(tl.M0v, float(kTileHalfCols), tl.Ub);
+                                tl.Vb = fmaf(tl.M4v, float(kTileHalfCols), tl.Vb);
+                                tl.Wb = fmaf(tl.M8v, float(kTileHalfCols), tl.Wb);
+                            }
 #undef VORS_TSTEP
                             __syncwarp();  // all lanes are done with this slot: the next iteration may refill it
                             ring_slot = (ring_slot + 1 == kStages) ? 0u : ring_slot + 1;
                             ring_parity ^= (ring_slot == 0) ? 1u : 0u;
-                            n_slots += kTileSlots;
+                            n_slots += kTileCols * rows_live;
                             tx += dtx;
                             ty += dty;
                             if (ty >= tiles_y) {
@@ -1156,7 +1193,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                             n_slots += kStageCand;
                         }
                     }
-                    if constexpr (kTiled) {  // the last two words of the last tile (slots 10 % 3 and 11 % 3) are still in flight
+                    if constexpr (kTiled) {  // the last two words of the last tile (slots 4 % 3 and 5 % 3) are still in flight
                         tile_back(f1, acc);
                         tile_back(f2, acc);
                     } else {
@@ -1166,6 +1203,17 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                     const long long t_hot = clock64();
 #endif
                     int n_bad = df.n_bad;
+                    if (df.n_near > 0) {  // warp-uniform
+                        int n_fix = 0;
+                        Acc<kHuber> tmp = acc;  // only this copy has its address taken: `acc` itself stays in registers in the hot loop
+                        deferred_pass<kSkew, kHuber, kTiled>(warp, lane, gw, TW, n_stages,
+                                                             (!kTiled && n_words <= kSmallWordsPerWarp * TW) ? n_words : 0, lj.defer, lj.defer_far, df.n_near,
+                                                             reinterpret_cast<uint32_t*>(&S.ring[warp][0]), hs, &tmp, &n_fix, &df.any_flip);
+                        acc = tmp;
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) n_fix += __shfl_xor_sync(0xffffffffu, n_fix, d);
+                        n_bad -= n_fix;
+                    }
                     if (df.any_flip) {  // warp-uniform: fold this warp's per-thread +-J J^T sums into its f64 slot, re-zero them
 #pragma unroll
                         for (int c = 0; c < 21; ++c) {
@@ -1175,16 +1223,6 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                             for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
                             if (lane == 0) S.hout[warp][c] += double(v);
                         }
-                    }
-                    if (df.n_near > 0) {  // warp-uniform
-                        int n_fix = 0;
-                        Acc<kHuber> tmp = acc;  // only this copy has its address taken: `acc` itself stays in registers in the hot loop
-                        deferred_pass<kSkew, kHuber, kTiled>(warp, lane, gw, TW, n_stages, lj.defer, df.wlist, df.n_words,
-                                             reinterpret_cast<uint32_t*>(&S.ring[warp][0]), &tmp, &n_fix);
-                        acc = tmp;
-#pragma unroll
-                        for (int d = 16; d > 0; d >>= 1) n_fix += __shfl_xor_sync(0xffffffffu, n_fix, d);
-                        n_bad -= n_fix;
                     }
 #if VORS_TIMING
                     const long long t_def = clock64();
@@ -1235,8 +1273,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                         } else {
 #pragma unroll
                             for (int w = 0; w < kWarps; ++w) {
-                                s += S.hout[w][v - kRawH] + S.hout_pass[w][v - kRawH];  // hout: cumulative over the level's passes
-                                S.hout_pass[w][v - kRawH] = 0.0;
+                                s += S.hout[w][v - kRawH];  // cumulative over the level's passes
                             }
                         }
                         if (team > 1)
@@ -1340,7 +1377,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                 for (int i = tid; i < n_slots_flow; i += kConsumers) {
                     const SlotRec sr = load_slot<kTiled>(lj.pts, lj.tiles_y, i);
                     const float rho = sr.rho, x = sr.x, y = sr.y;
-                    if (kTiled && !(rho == rho)) continue;  // no depth / outside the image
+                    if (kTiled && !(rho == rho && rho != 0.0f)) continue;  // no depth / outside the image
                     const float U = fmaf(S.M[0], x, fmaf(S.M[1], y, fmaf(S.M[3], rho, S.M[2])));
                     const float V = fmaf(S.M[4], x, fmaf(S.M[5], y, fmaf(S.M[7], rho, S.M[6])));
                     const float W = fmaf(S.M[8], x, fmaf(S.M[9], y, fmaf(S.M[11], rho, S.M[10])));
@@ -1375,6 +1412,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
             R.n_passes = S.n_passes;
             R.trace_len = S.trace_len < kTraceCap ? S.trace_len : kTraceCap;
             R.point_passes = S.point_passes;
+            R.t_end_ns = global_timer_ns();
         }
         __syncthreads();
     }

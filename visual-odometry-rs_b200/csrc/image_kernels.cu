@@ -515,7 +515,8 @@ __global__ void __launch_bounds__(kTileSlots) k_tile_records(const Geom g, const
     const int j = threadIdx.x / kTileRows, lane = threadIdx.x % kTileRows;
     const int x = kTileCols * tx + j, y = kTileRows * ty + lane;
     const int R = g.rows[l], C = g.cols[l];
-    float rho = __int_as_float(0x7fc00000);
+    // rows below the image: zero inverse depth (the align kernel's dead lanes); columns beyond it and pixels without depth: NaN
+    float rho = y < R ? __int_as_float(0x7fc00000) : 0.0f;
     uint32_t gr = 0u;
     unsigned short tm = 0;
     if (x < C && y < R) {
@@ -551,7 +552,7 @@ __global__ void __launch_bounds__(512) k_h_total_tiled(const Geom g, const Level
         const int st = i / kTileSlots, j = (i / kTileRows) % kTileCols, ln = i % kTileRows;
         const uint32_t* w = lvl + size_t(st) * kTileWords;
         const float rho = __uint_as_float(w[tile_rho_word(j, ln)]);
-        if (isnan(rho)) continue;
+        if (isnan(rho) || rho == 0.0f) continue;
         ++valid;
         const int tx = st / tiles_y, ty = st - tx * tiles_y;
         const uint32_t gr = w[tile_grad_word(j, ln)];

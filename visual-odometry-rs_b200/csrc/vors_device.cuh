@@ -15,10 +15,12 @@
 //   * DENSE keyframes with zero skew and plain L2 (the benchmarked configuration) use TILED records with IMPLICIT coordinates
 //     instead: a level is cut into tiles of 32 rows x 12 columns; one tile = one ring stage of 384 slots, slot (j, lane) =
 //     pixel (x = 12 tx + j, y = 32 ty + lane), tiles ordered column-of-tiles major (stage c = tx * tiles_y + ty).  A stage is
-//     3840 bytes: inverse depths f32 [3][32][4] (lane-contiguous quads: one 16-byte shared load brings four words' values),
-//     gradients half2 [3][32][4], template values f16 [3][32][4] = 10 B per slot; pixels outside the image or without depth
-//     carry a NaN inverse depth (never inside, never in H_total).  x, y never travel: they follow from the stage and lane.
-//     (12 columns: a multiple of the three-deep software pipeline of the align kernel's hot loop.)
+//     3840 bytes: inverse depths f32 [2][32][6] (the six values a lane needs for half a tile are contiguous: three 8-byte
+//     shared loads), gradients half2 [2][32][6], template values f16 [2][32][6] = 10 B per slot; pixels outside the image
+//     or without depth carry a NaN inverse depth (never inside, never in H_total), rows below the image a zero one (the
+//     align kernel's dead lanes).  x, y never travel: they follow from the stage and lane.
+//     (12 columns = two half tiles of six words: a multiple of the three-slot software pipeline of the align kernel's hot
+//     loop, whose unrolled body of six words still fits the instruction cache.)
 //   * the frame pyramids the align kernel SAMPLES live in gather-enabled 2D CUDA arrays ("atlas pages", u8 texels read as
 //     texel / 255, or f16 with -DVORS_TEX_F16=1): texture x = image y.  Stream s, level l occupies the cell at
 //     (ox, oy) = ((s % per_row) * cell_w, (s / per_row) * cell_h + lvl_y[l]) with cell_w = rows_0 + 2, lvl_y[l] = sum_{k<l}
@@ -63,7 +65,8 @@ constexpr int kTileCols = 12;
 constexpr int kTileSlots = kTileRows * kTileCols;
 constexpr int kTileBytes = kTileSlots * 10;  // rho f32 | grad half2 | template f16
 constexpr int kTileWords = kTileBytes / 4;
-static_assert(kTileCols % 4 == 0 && kTileCols % 3 == 0, "quads of words per 16-byte load; three-deep software pipeline");
+constexpr int kTileHalfCols = kTileCols / 2;  // words per unrolled half tile
+static_assert(kTileCols % 2 == 0 && kTileHalfCols % 3 == 0 && kTileHalfCols % 2 == 0, "half tiles of a multiple of three words (pipeline slots), even (8-byte loads)");
 
 struct Geom {
     int L;
@@ -86,7 +89,9 @@ struct Geom {
 };
 
 // word offsets of slot (j, lane) of a tile inside its kTileWords-word stage
-__host__ __device__ __forceinline__ int tile_rho_word(int j, int lane) { return (j >> 2) * 128 + lane * 4 + (j & 3); }
+__host__ __device__ __forceinline__ int tile_rho_word(int j, int lane) {
+    return (j / kTileHalfCols) * (kTileRows * kTileHalfCols) + lane * kTileHalfCols + j % kTileHalfCols;
+}
 __host__ __device__ __forceinline__ int tile_grad_word(int j, int lane) { return kTileSlots + tile_rho_word(j, lane); }
 __host__ __device__ __forceinline__ int tile_tmpl_half(int j, int lane) { return 4 * kTileSlots + tile_rho_word(j, lane); }  // index in halves
 
@@ -140,6 +145,7 @@ struct AlignResult {
     int n_passes;
     int trace_len;
     unsigned long long point_passes;
+    unsigned long long t_begin_ns, t_end_ns;  // %globaltimer when the team picked the job up / finished it (load-balance diagnosis)
     // pass_only outputs
     float pass_energy;
     int pass_n_inside;
