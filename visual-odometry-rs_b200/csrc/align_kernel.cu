@@ -74,7 +74,8 @@ constexpr int kRingWords = kStageWords > kTileWords ? kStageWords : kTileWords; 
 constexpr uint32_t kRingBytes = kRingWords * 4;
 constexpr int kTileWordsBm = kTileSlots / 32;  // bitmap words per tile
 constexpr int kHsmStride = 21;  // odd: scalar accesses of a warp hit 32 distinct banks
-constexpr int kStashCap = 16;   // boundary-band candidates a warp stashes per pass (beyond that: bitmap scan)
+constexpr int kStashCap = 16;   // boundary-band candidates a warp stashes per pass
+constexpr int kNearWords = 32;  // beyond that: flagged bitmap words a warp remembers per pass; beyond that: bitmap scan
 static_assert(kStageCand == kPtAlign, "levels are padded to whole ring stages");
 
 struct LmShared {
@@ -107,6 +108,7 @@ struct LmShared {
     // boundary-band candidates flagged by each warp in this pass, stashed with what their exact re-evaluation needs
     // (slot, a = x - cx, b = y - cy, inverse depth, gradient bits, template value): no record is read twice
     uint32_t stash[kWarps][kStashCap][6];
+    uint32_t near_words[kWarps][2 * kNearWords];  // (word, mask) pairs flagged by each warp in this pass (second tier, see deferred_pass)
     alignas(8) unsigned long long full_bar[kWarps][kStages];
     alignas(128) float ring[kWarps][kStages * kRingWords];
     // per-thread J J^T accumulators of the hot loop (candidates that changed sides of the frame border): 21 floats at an
@@ -367,9 +369,8 @@ template <bool kSkew>
 __device__ __forceinline__ void add_outside(float sign, uint32_t gr, float a, float b, float rho, const Intrinsics& k, float* hs);
 
 // One deferred candidate: the reference's own warp decides (lm_optimizer.rs:213-231).  Inside -> full evaluation into `acc`.
-// Outside -> it joins the candidates that are outside for sure: its bit is set in the level's far bitmap and its J J^T goes
-// to the thread's shared-memory accumulators like any other candidate that changed sides (H = H_total - H_outside); the
-// next pass takes it out again if it is no longer outside.
+// Its side is kept in the level's far bitmap like that of the candidates that are outside for sure: when the exact verdict
+// differs from the bit, the bit flips and -+J J^T goes to the thread's shared-memory accumulators (H = H_total - H_outside).
 template <bool kSkew, bool kHuber>
 __device__ __forceinline__ void eval_deferred(int slot, float ca, float cb, float rho, uint32_t gr, float tmpl, const LevelConst& lc,
                                               const Pose& model, Acc<kHuber>& acc, int& fixed, uint32_t* far_bitmap, float* hs, int& any_flip) {
@@ -380,6 +381,18 @@ __device__ __forceinline__ void eval_deferred(int slot, float ca, float cb, floa
     const float2 uv = warp_exact(model, k, rintf(ca + lc.cx), rintf(cb + lc.cy), rho);
     // 0 <= floor(u) < W-2  <=>  0 <= u < W-2 (W-2 is an integer); NaN compares false -> outside
     const bool inside = (uv.x >= 0.0f) && (uv.x < lc.wm2) && (uv.y >= 0.0f) && (uv.y < lc.hm2);
+    if (!kHuber) {
+        const unsigned bit = 1u << (slot & 31);
+        const bool was_outside = (__ldcg(far_bitmap + (slot >> 5)) & bit) != 0u;
+        if (was_outside == inside) {  // changed sides
+            if (inside)
+                atomicAnd(far_bitmap + (slot >> 5), ~bit);
+            else
+                atomicOr(far_bitmap + (slot >> 5), bit);
+            add_outside<kSkew>(inside ? -1.0f : 1.0f, gr, ca, cb, rho, k, hs);
+            any_flip = 1;
+        }
+    }
     if (inside) {
         const float fu = floorf(uv.x), fv = floorf(uv.y);
         const float a = uv.x - fu, b = uv.y - fv;
@@ -404,10 +417,6 @@ __device__ __forceinline__ void eval_deferred(int slot, float ca, float cb, floa
                 accumulate_moments(acc, gu, gv, ca, cb, rho, r);
             }
         }
-    } else if (!kHuber) {
-        atomicOr(far_bitmap + (slot >> 5), 1u << (slot & 31));
-        add_outside<kSkew>(1.0f, gr, ca, cb, rho, k, hs);
-        any_flip = 1;
     }
 }
 
@@ -418,8 +427,8 @@ __device__ __forceinline__ void eval_deferred(int slot, float ca, float cb, floa
 // `small_words` > 0: the level went through the small-level path (its `small_words` bitmap words dealt round-robin to the warps).
 template <bool kSkew, bool kHuber, bool kTiled>
 __device__ __noinline__ void deferred_pass(int warp, int lane, int first_stage, int stage_stride, int n_stages, int small_words,
-                                           uint32_t* __restrict__ bitmap, uint32_t* __restrict__ far_bitmap, int n_near, uint32_t* scratch,
-                                           float* hs, Acc<kHuber>* acc_io, int* n_fix, int* any_flip_io) {
+                                           uint32_t* __restrict__ bitmap, uint32_t* __restrict__ far_bitmap, int n_near, const uint32_t* wlist,
+                                           int n_flagged_words, uint32_t* scratch, float* hs, Acc<kHuber>* acc_io, int* n_fix, int* any_flip_io) {
     LmShared& S = lm_shared();
     const LevelConst& lc = s_lc;
     Acc<kHuber> acc = *acc_io;
@@ -433,8 +442,23 @@ __device__ __noinline__ void deferred_pass(int warp, int lane, int first_stage, 
                                          S.cand_model, acc, fixed, far_bitmap, hs, any_flip);
         }
     } else {
-        // One round: every lane brings one flagged bitmap word (`mask` over the 32 slots starting at slot `base`); the set bits of
-        // the whole warp are compacted into `scratch` (at most 1024 entries) and evaluated one candidate per lane and step.
+        // The flagged slots are first gathered into one list (`scratch`, at most kListCap entries between two flushes) and then
+        // evaluated 32 at a time, whatever their spread over the bitmap words: a boundary ROW puts one slot into every word it
+        // crosses, a boundary COLUMN 32 slots into one word.
+        constexpr int kListCap = 1024;
+        int n_list = 0;  // warp-uniform
+        auto flush = [&]() {
+            __syncwarp();
+            for (int e = lane; e < n_list; e += 32) {
+                const int slot = int(scratch[e]);
+                const SlotRec sr = load_slot<kTiled>(lc.pts, lc.tiles_y, slot);
+                eval_deferred<kSkew, kHuber>(slot, sr.x - lc.cx, sr.y - lc.cy, sr.rho, sr.gr, sr.tmpl, lc, S.cand_model, acc, fixed, far_bitmap, hs,
+                                             any_flip);
+            }
+            __syncwarp();
+            n_list = 0;
+        };
+        // every lane brings one flagged bitmap word: `mask` over the 32 slots starting at slot `base`
         auto round = [&](uint32_t mask, int base) {
             const int cnt = __popc(mask);
             int incl = cnt;
@@ -444,21 +468,27 @@ __device__ __noinline__ void deferred_pass(int warp, int lane, int first_stage, 
                 if (lane >= d) incl += t;
             }
             const int total = __shfl_sync(0xffffffffu, incl, 31);
-            int off = incl - cnt;
+            if (n_list + total > kListCap) flush();
+            int off = n_list + incl - cnt;
             while (mask) {
                 scratch[off++] = uint32_t(base) + uint32_t(__ffs(mask) - 1);
                 mask &= mask - 1u;
             }
-            __syncwarp();
-            for (int e = lane; e < total; e += 32) {
-                const int slot = int(scratch[e]);
-                const SlotRec sr = load_slot<kTiled>(lc.pts, lc.tiles_y, slot);
-                eval_deferred<kSkew, kHuber>(slot, sr.x - lc.cx, sr.y - lc.cy, sr.rho, sr.gr, sr.tmpl, lc, S.cand_model, acc, fixed, far_bitmap, hs,
-                                             any_flip);
-            }
-            __syncwarp();
+            n_list += total;
         };
-        // this warp's bitmap words, one per lane and round: the words of its stages, or its share of a small level's words
+        if (n_flagged_words <= kNearWords) {
+            // second tier (e.g. a whole boundary column exactly on the inside-test boundary: one word, 32 candidates): the flagged
+            // words were remembered, one per lane
+            uint32_t word = 0u, mask = 0u;
+            if (lane < n_flagged_words) {
+                word = wlist[2 * lane];
+                mask = wlist[2 * lane + 1];
+                bitmap[word] = 0u;
+            }
+            round(mask, int(word) * 32);
+            flush();
+        } else {
+        // third tier: this warp's bitmap words, one per lane and round: the words of its stages, or its share of a small level's words
         constexpr int kW = kTiled ? kTileWordsBm : kStageWordsBm;
         const int my_words = small_words > 0 ? (small_words > first_stage ? (small_words - first_stage + stage_stride - 1) / stage_stride : 0)
                                              : (first_stage < n_stages ? ((n_stages - first_stage + stage_stride - 1) / stage_stride) * kW : 0);
@@ -473,6 +503,8 @@ __device__ __noinline__ void deferred_pass(int warp, int lane, int first_stage, 
             }
             if (!__any_sync(0xffffffffu, mask != 0u)) continue;
             round(mask, word * 32);
+        }
+        flush();
         }
         // `scratch` is ring memory: order these generic-proxy accesses before the next pass's bulk copies (async proxy)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -547,6 +579,8 @@ struct Defer {
     int n_bad;         // slots of this pass redirected to the zero page so far
     int n_near;        // of which flagged in `near`
     uint32_t* stash;   // this warp's stash of the flagged candidates (shared memory, kStashCap entries of 6 words)
+    int n_words;       // bitmap words flagged in `near` during this pass
+    uint32_t* wlist;   // (word, mask) of the first kNearWords of them (shared memory)
     int any_flip;      // this warp added to its hsm accumulators during this pass
     int first_pass;    // first pass of the level: the far bitmap holds nothing yet
 };
@@ -610,15 +644,25 @@ __device__ __forceinline__ void rare_slots(unsigned not_ok, float u, float v, fl
     // padding slots and pixels without depth carry a NaN inverse depth: never `far`, and they need no second look
     const unsigned live_mask = __ballot_sync(0xffffffffu, rho == rho);
     const unsigned far_mask = __ballot_sync(0xffffffffu, far), near_mask = not_ok & ~far_mask & live_mask;
-    const unsigned flips = kHuber ? 0u : far_mask ^ old_far;  // (Huber weights: H is summed directly, nothing to maintain)
+    // candidates in the boundary band keep the side they were on until their exact evaluation decides (deferred_pass): a
+    // candidate sitting ON the boundary (static camera) then costs nothing here from its second pass on
+    const unsigned new_far = (far_mask & ~near_mask) | (old_far & near_mask);
+    const unsigned flips = kHuber ? 0u : new_far ^ old_far;  // (Huber weights: H is summed directly, nothing to maintain)
     if (flips) {
         const float sign = ((flips >> lane) & 1u) ? (far ? 1.0f : -1.0f) : 0.0f;
         add_outside<kSkew>(sign, gr, a, b, rho, k, hs);
         df.any_flip = 1;
     }
-    if (lane == 0 && flips) df.far[word] = far_mask;
+    if (lane == 0 && flips) df.far[word] = new_far;
     if (near_mask) {  // boundary band / NaN coordinates of a live candidate: see deferred_pass
-        if (lane == 0) df.near[word] = near_mask;
+        if (lane == 0) {
+            df.near[word] = near_mask;
+            if (df.n_words < kNearWords) {
+                df.wlist[2 * df.n_words] = uint32_t(word);
+                df.wlist[2 * df.n_words + 1] = near_mask;
+            }
+        }
+        df.n_words += 1;
         const int at = df.n_near + __popc(near_mask & ((1u << lane) - 1u));
         if (((near_mask >> lane) & 1u) && at < kStashCap) {
             uint32_t* e = df.stash + 6 * at;
@@ -989,6 +1033,8 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                     df.n_bad = 0;
                     df.n_near = 0;
                     df.stash = &S.stash[warp][0][0];
+                    df.n_words = 0;
+                    df.wlist = S.near_words[warp];
                     df.any_flip = 0;
                     df.first_pass = __shfl_sync(0xffffffffu, S.init_phase, 0);
                     float* hs = S.hsm[tid];
@@ -1207,7 +1253,7 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                         int n_fix = 0;
                         Acc<kHuber> tmp = acc;  // only this copy has its address taken: `acc` itself stays in registers in the hot loop
                         deferred_pass<kSkew, kHuber, kTiled>(warp, lane, gw, TW, n_stages,
-                                                             (!kTiled && n_words <= kSmallWordsPerWarp * TW) ? n_words : 0, lj.defer, lj.defer_far, df.n_near,
+                                                             (!kTiled && n_words <= kSmallWordsPerWarp * TW) ? n_words : 0, lj.defer, lj.defer_far, df.n_near, df.wlist, df.n_words,
                                                              reinterpret_cast<uint32_t*>(&S.ring[warp][0]), hs, &tmp, &n_fix, &df.any_flip);
                         acc = tmp;
 #pragma unroll
