@@ -54,6 +54,9 @@ namespace {
 #ifndef VORS_STAGES
 #define VORS_STAGES 2
 #endif
+#ifndef VORS_OLD_SERIAL
+#define VORS_OLD_SERIAL 0  // 1: the round-1 serial LM round (one lane, IEEE divisions) instead of serial_round
+#endif
 #ifndef VORS_FRND
 #define VORS_FRND 0     // 1: floor by FRND.FLOOR (one XU-pipe instruction) instead of the round-down magic-number add + subtract
 #endif
@@ -274,6 +277,7 @@ struct LevelConst {
     const uint32_t* pts;        // the level's chunk-blocked candidates (deferred pass)
     Intrinsics k;
     double inv_fx, inv_fy, k01;  // 1/fx, 1/fy, -s/(fx fy): the f64 divisions of the per-pass serial part, done once per level
+    double ga[6], gb[6];         // g from the gradient moments (serial_round)
     float huber_delta;
 };
 
@@ -914,6 +918,216 @@ __device__ __forceinline__ float warp_matrix_entry(int e, const Pose& m, const L
     return float(r == 0 ? fx * a0 + s * a1 : r == 1 ? fy * a1 : a2);
 }
 
+// ---- the serial part of an LM round, warp-uniform --------------------------------------------------------------------------
+// Every lane of the serial warp runs the same scalar program on the same values (no divergent region, no round trip through
+// shared memory between its stages, no call): the chain is latency-bound, so what counts is its length in dependent
+// instructions.  Divisions and square roots are a MUFU seed plus Newton steps (<= 1 ulp) instead of the IEEE sequences with
+// their slow-path checks: the solver's result is not bit-compatible with nalgebra's anyway (FMA contraction), and its
+// round-off is five orders of magnitude below the step it computes.
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+__device__ __forceinline__ float fast_rsqrt(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r * fmaf(-0.5f * x, r * r, 1.5f);  // one Newton step
+}
+// nalgebra 0.17 `Matrix6::cholesky()` + `solve` (lm_optimizer.rs:131-134) in the operation order of lie.cuh's
+// cholesky6_solve, with the fast reciprocals above.  A: lower triangle, row-major 6x6.
+__device__ __forceinline__ bool cholesky6_solve_fast(float (&A)[36], float (&b)[6]) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+#pragma unroll
+        for (int k = 0; k < j; ++k) {
+            const float factor = -A[j * 6 + k];
+#pragma unroll
+            for (int i = j; i < 6; ++i) A[i * 6 + j] = fmaf(factor, A[i * 6 + k], A[i * 6 + j]);
+        }
+        const float diag = A[j * 6 + j];
+        if (!(diag > 0.0f)) return false;
+        const float inv = fast_rsqrt(diag);
+        A[j * 6 + j] = inv;  // 1 / L_jj: every later use of the diagonal is a division by it
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) A[i * 6 + j] *= inv;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const float coeff = b[i] * A[i * 6 + i];
+        b[i] = coeff;
+#pragma unroll
+        for (int r = i + 1; r < 6; ++r) b[r] = fmaf(-coeff, A[r * 6 + i], b[r]);
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        float dot = 0.0f;
+#pragma unroll
+        for (int r = i + 1; r < 6; ++r) dot = fmaf(A[r * 6 + i], b[r], dot);
+        b[i] = (b[i] - dot) * A[i * 6 + i];
+    }
+    return true;
+}
+// src/math/se3.rs:65-95 `exp` (lie.cuh se3_exp) with the fast reciprocals; the trigonometric branch (theta >= 0.01, the first
+// rounds of a coarse level at most) keeps the accurate sinf / cosf: (1 - cos theta) / theta^2 cancels.
+__device__ __forceinline__ Pose se3_exp_fast(const float (&xi)[6]) {
+    const float v0 = xi[0], v1 = xi[1], v2 = xi[2];
+    const float wx = xi[3], wy = xi[4], wz = xi[5];
+    const float theta_2 = wx * wx + wy * wy + wz * wz;
+    float real_factor, imag_factor, c1, c2;
+    if (theta_2 < 1e-2f * 1e-2f) {
+        real_factor = 1.0f - 0.125f * theta_2;
+        imag_factor = 0.5f - (1.0f / 48.0f) * theta_2;
+        c1 = 0.5f - (1.0f / 24.0f) * theta_2;
+        c2 = (1.0f / 6.0f) - (1.0f / 120.0f) * theta_2;
+    } else {
+        const float theta = sqrtf(theta_2);
+        const float half_theta = 0.5f * theta;
+        real_factor = cosf(half_theta);
+        imag_factor = sinf(half_theta) / theta;
+        c1 = (1.0f - cosf(theta)) / theta_2;
+        c2 = (theta - sinf(theta)) / (theta * theta_2);
+    }
+    const float w11 = wx * wx, w12 = wx * wy, w13 = wx * wz, w22 = wy * wy, w23 = wy * wz, w33 = wz * wz;
+    Pose out;
+    // V = I + c1 Omega + c2 Omega^2 applied to v
+    out.t.x = ((1.0f + c2 * (-w22 - w33)) * v0 + (c1 * -wz + c2 * w12) * v1) + (c1 * wy + c2 * w13) * v2;
+    out.t.y = ((c1 * wz + c2 * w12) * v0 + (1.0f + c2 * (-w11 - w33)) * v1) + (c1 * -wx + c2 * w23) * v2;
+    out.t.z = ((c1 * -wy + c2 * w13) * v0 + (c1 * wx + c2 * w23) * v1) + (1.0f + c2 * (-w11 - w22)) * v2;
+    const Quat q{imag_factor * wx, imag_factor * wy, imag_factor * wz, real_factor};
+    const float inv_n = fast_rsqrt(quat_norm2(q));  // UnitQuaternion::from_quaternion normalises
+    out.q = {q.i * inv_n, q.j * inv_n, q.k * inv_n, q.w * inv_n};
+    return out;
+}
+
+// g entries of the finished pass from the gradient moments: g[t] = ga[t] * m[gi[t]] + gb[t] * m[gj[t]] (see accumulate_moments;
+// inverse_compositional.rs:326-340 with zero skew).  The coefficient pairs are per-level constants (LevelConst::ga, gb).
+__constant__ int c_gi[6] = {kSrp, kSrq, kSrs, kSbs, kSas, kSaq};
+__constant__ int c_gj[6] = {kSrp, kSrq, kSrs, kSq, kSp, kSbp};
+
+// One LM round after a pass: finish (sum r^2, n_inside, g, H from the raw totals), decide (init / eval / stop_criterion,
+// lm_optimizer.rs:113-192), step (:123-136) and the next candidate model's warp matrix.  Run by all 32 lanes of the serial warp.
+template <bool kSkew, bool kHuber>
+__device__ __noinline__ void serial_round(const AlignParams& P, int job_idx, int lvl, bool writer, int lane, int n_level, int pass_only) {
+    LmShared& S = lm_shared();
+    const LevelConst& lc = s_lc;
+    const double* raw = S.raw;
+    // ---- finish: lane t holds entry t of (sum r^2, n_inside, g[6], H[21])
+    double mine = 0.0;
+    if (lane < kNumAcc) {
+        if (kHuber || kSkew || lane < 2) {
+            mine = raw[lane];
+        } else if (lane < 8) {
+            const int t = lane - 2;
+            mine = lc.ga[t] * raw[2 + c_gi[t]] + lc.gb[t] * raw[2 + c_gj[t]];
+        }
+        if (!kHuber && lane >= 8)
+            // H over the inside set = H_total (all candidates, per keyframe level) - H_outside; an empty inside set must give an
+            // exactly zero H (the reference then fails its Cholesky, lm_optimizer.rs:131-133)
+            mine = raw[1] > 0.0 ? S.h_total[lane - 8] - raw[kRawH + (lane - 8)] : 0.0;
+        S.tot[lane] = mine;
+    }
+    if (lane == 0) S.point_passes += (unsigned long long)n_level;
+    if (pass_only) {
+        if (lane == 0) {
+            S.n_passes += 1;
+            S.cont = 0;
+        }
+        return;
+    }
+    // ---- decide (every lane, same values)
+    const float mine_f = float(mine);
+    const int n_inside = int(__shfl_sync(0xffffffffu, mine, 1));
+    // energy = energy_sum / residuals.len() as f32 (lm_optimizer.rs:85); 0/0 = NaN when nothing is inside
+    const float E = __shfl_sync(0xffffffffu, mine_f, 0) / float(n_inside);
+    const int init_phase = S.init_phase, iter = S.iter;
+    const float lam_old = S.lam, keptE = S.keptE;
+    const float lam_used = init_phase ? P.lm_coef_init : lam_old;
+    float lam = lam_old;
+    bool stop, accepted = true;
+    if (init_phase) {
+        lam = P.lm_coef_init;
+        stop = false;
+    } else {
+        const bool rejected = E > keptE;  // lm_optimizer.rs:144 (NaN compares false -> accepted)
+        accepted = !rejected;
+        const bool too_many = P.fixed_iters ? (iter >= P.fixed_iters) : (iter > P.max_iters);
+        if (rejected) {
+            stop = too_many;
+            if (!too_many) lam = lam_old * P.lm_coef_reject_mult;
+        } else if (too_many) {
+            stop = true;
+        } else {
+            const float d_energy = keptE - E;
+            stop = P.fixed_iters ? false : !(d_energy > P.energy_delta_stop);
+            lam = P.lm_coef_accept_mult * lam_old;
+        }
+    }
+    const int trace_len = S.trace_len;
+    if (lane == 0 && writer && P.trace && trace_len < kTraceCap) {
+        vors_trace_rec& t = P.trace[size_t(job_idx) * kTraceCap + trace_len];
+        t.level = lvl;
+        t.iter = init_phase ? 0 : iter;
+        t.energy = E;
+        t.n_inside = n_inside;
+        t.lm_coef = lam_used;
+        t.accepted = accepted ? 1 : 0;
+    }
+    // kept state = last accepted evaluation; every lane keeps g, H and the kept model in registers for the step below
+    float g[6], H[21];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) g[c] = accepted ? __shfl_sync(0xffffffffu, mine_f, 2 + c) : S.keptg[c];
+#pragma unroll
+    for (int c = 0; c < 21; ++c) H[c] = accepted ? __shfl_sync(0xffffffffu, mine_f, 8 + c) : S.keptH[c];
+    const Pose kept = accepted ? S.cand_model : S.kept_model;
+    // every lane has read the round's state: only now may it be overwritten (the lanes of a warp are not in lock step)
+    __syncwarp();
+    if (accepted) {
+        if (lane >= 2 && lane < 8) S.keptg[lane - 2] = mine_f;
+        if (lane >= 8 && lane < kNumAcc) S.keptH[lane - 8] = mine_f;
+        if (lane == 0) {
+            S.keptE = E;
+            S.kept_model = kept;
+        }
+    }
+    if (lane == 0) {
+        S.n_passes += 1;
+        S.trace_len = trace_len + 1;
+        S.lam = lam;
+        S.init_phase = 0;
+        S.iter = init_phase ? 0 : iter;
+    }
+    if (stop) {
+        if (lane == 0) S.cont = 0;
+        return;
+    }
+    // ---- step (lm_optimizer.rs:123-136)
+    float A[36], b[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) A[r * 6 + c] = H[tri(c, r)];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) A[c * 6 + c] *= 1.0f + lam;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) b[c] = g[c];
+    if (!cholesky6_solve_fast(A, b)) {
+        if (lane == 0) {
+            S.iter = (init_phase ? 0 : iter) + 1;
+            S.failed = 1;
+            S.cont = 0;
+        }
+        return;
+    }
+    const Pose cand = pose_renormalize(pose_mul(kept, pose_inverse(se3_exp_fast(b))));
+    if (lane == 0) {
+        S.iter = (init_phase ? 0 : iter) + 1;
+        S.cand_model = cand;
+        S.cont = 1;
+    }
+    if (lane < 12) S.M[lane] = warp_matrix_entry(lane, cand, lc);
+}
+
 template <bool kSkew, bool kHuber, bool kTiled>
 #ifdef VORS_MAXREG
 __global__ void __maxnreg__(VORS_MAXREG) k_align(const AlignParams P) {
@@ -943,7 +1157,13 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
     for (int i = tid; i < kConsumers * kHsmStride; i += kBlock) (&S.hsm[0][0])[i] = 0.0f;
     __syncthreads();
 
-    for (int job_idx = team_id; job_idx < P.n_jobs; job_idx += n_teams) {
+    // Jobs: one per team when the batch fits the device; a larger batch is handed out dynamically (team == 1 only), so that a
+    // CTA that finishes a cheap alignment early takes the next one instead of idling behind the slowest: the spread of the
+    // per-alignment times (border candidates, boundary-band work) otherwise costs ~10 % at the end of every launch.
+    const bool dynamic_jobs = P.job_counter != nullptr && team == 1 && P.n_jobs > n_teams;
+    __shared__ int s_next_job;
+    for (int job_idx = team_id;;) {
+        if (job_idx >= P.n_jobs) break;
         const AlignJob& job = P.jobs[job_idx];
         const bool writer = (rank == 0);
         if (writer && tid == 0) P.results[job_idx].t_begin_ns = global_timer_ns();
@@ -996,6 +1216,15 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                 c.inv_fy = 1.0 / double(k.fy);
                 c.k01 = -double(k.s) / (double(k.fx) * double(k.fy));
                 c.huber_delta = P.huber_delta;
+                {
+                    const double fu = k.fx, fv = k.fy;
+                    const double ga[6] = {fu, fv, -1.0, -c.inv_fy, c.inv_fx, fv * c.inv_fx};
+                    const double gb[6] = {0.0, 0.0, 0.0, -fv, fu, -(fu * c.inv_fy)};
+                    for (int t = 0; t < 6; ++t) {
+                        c.ga[t] = ga[t];
+                        c.gb[t] = gb[t];
+                    }
+                }
                 s_lc = c;
                 S.cand_model = S.out_model;
                 S.init_phase = 1;  // also: the level's far bitmap and H_outside start empty
@@ -1348,11 +1577,9 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
 #if VORS_TIMING
                     const long long ts1 = clock64();
 #endif
+#if VORS_OLD_SERIAL
                     if (lane < kNumAcc) S.tot[lane] = finish_entry<kSkew, kHuber>(lane, S.raw, s_lc, S.h_total);
                     __syncwarp();
-#if VORS_TIMING
-                    const long long ts2 = clock64();
-#endif
                     if (lane == 0) {
                         S.point_passes += (unsigned long long)n;
                         if (job.pass_only) {
@@ -1363,15 +1590,15 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
                         }
                     }
                     __syncwarp();
-#if VORS_TIMING
-                    const long long ts3 = clock64();
-#endif
                     if (S.cont && lane < 12) S.M[lane] = warp_matrix_entry(lane, S.cand_model, s_lc);
+#else
+                    serial_round<kSkew, kHuber>(P, job_idx, lvl, writer, lane, n, job.pass_only);
+#endif
 #if VORS_TIMING
                     __syncwarp();
                     if (lane == 0 && lvl < 8) {
                         const long long ts4 = clock64();
-                        S.dbgs[lvl][0] += ts1 - ts0; S.dbgs[lvl][1] += ts2 - ts1; S.dbgs[lvl][2] += ts3 - ts2; S.dbgs[lvl][3] += ts4 - ts3;
+                        S.dbgs[lvl][0] += ts1 - ts0; S.dbgs[lvl][1] += 0; S.dbgs[lvl][2] += ts4 - ts1; S.dbgs[lvl][3] += 0;
                     }
 #endif
                 }
@@ -1459,6 +1686,13 @@ __global__ void __launch_bounds__(kBlock, kMinCtasPerSm) k_align(const AlignPara
             R.trace_len = S.trace_len < kTraceCap ? S.trace_len : kTraceCap;
             R.point_passes = S.point_passes;
             R.t_end_ns = global_timer_ns();
+        }
+        if (dynamic_jobs) {
+            if (tid == 0) s_next_job = n_teams + int(atomicAdd(P.job_counter, 1u));
+            __syncthreads();
+            job_idx = s_next_job;
+        } else {
+            job_idx += n_teams;
         }
         __syncthreads();
     }

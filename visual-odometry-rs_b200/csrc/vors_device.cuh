@@ -165,6 +165,7 @@ struct AlignParams {
     AlignResult* results;
     vors_trace_rec* trace;  // n_jobs * kTraceCap, or nullptr
     TeamScratch* scratch;   // one per team (only touched when team > 1)
+    unsigned int* job_counter;  // zeroed before the launch: jobs beyond the first wave are handed out through it (team == 1)
     int n_jobs;
     int team;
     // LM constants (lm_optimizer.rs:115,157,173,179,186)
