@@ -2,7 +2,7 @@
 rounds / level, team_size 1: per frame and level the final energy and iteration decisions of the GPU against the oracle with
 f64 sums, and the pose distance.  VORS_NO_TILED=1 selects the generic records for the same comparison."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "visual-odometry-rs_b200"))
 import numpy as np, torch
 import bench

@@ -1,6 +1,6 @@
 """Diagnosis (GPU box): 296 replicas of one bench stream for a few steps: every replica must produce bit-identical poses."""
 import os, sys, ctypes as C
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "visual-odometry-rs_b200"))
 import numpy as np, torch
 import bench

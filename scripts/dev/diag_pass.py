@@ -1,7 +1,7 @@
 """Diagnosis (GPU box): one evaluation of level LVL of frame F of bench stream S at the oracle's own level-(LVL+1) model,
 tiled GPU records against the oracle; on a mismatch the keyframe depth is masked to sub-rectangles of tiles to localise it."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "visual-odometry-rs_b200"))
 import numpy as np, torch
 import bench

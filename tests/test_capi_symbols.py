@@ -38,7 +38,7 @@ def test_header_symbols_are_exported_and_bound(vb):
 
 
 def test_struct_layouts_match_header(vb):
-    # vors_config: 17 scalar 4-byte fields + dso_nb_target + reserved[3]
+    # vors_config: 23 scalar 4-byte fields (include/vors_b200.h)
     assert C.sizeof(vb.ConfigStruct) == 4 * 23
     assert C.sizeof(vb.Pose) == 28
     assert C.sizeof(vb.TraceRec) == 24

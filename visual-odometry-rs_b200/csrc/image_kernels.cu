@@ -708,7 +708,7 @@ void launch_tile_records(Launcher& L, const Geom& g, const Intrinsics* intr, con
     L.launches += 2;
 }
 void launch_atlas_fill(Launcher& L, const Geom& g, const uint8_t* pyr_slab, const AtlasPages& pages, const int* items, int m, int first) {
-    dim3 grid(grid_for(g.pix_total, 256, 64), m);
+    dim3 grid(grid_for(g.pix_total, 256, std::max(64, 148 * 8 / std::max(m, 1))), m);  // a single stream still fills the device
     k_atlas_fill<<<grid, 256, 0, L.stream>>>(g, pyr_slab, pages, items, first);
     ++L.launches;
 }
