@@ -183,6 +183,11 @@ int vors_batch_track_device(vors_batch* b, const double* depth_ts, const uint16_
 int vors_batch_track_device_next(vors_batch* b, const double* depth_ts, const uint16_t* depth_dev,
                                  const double* img_ts, const uint8_t* img_dev, const uint8_t* next_img_dev,
                                  int* status, vors_track_stats* stats);
+/* Forgets the frames announced by the last vors_batch_track_next / _device_next call and waits for their copy to finish:
+ * afterwards the announced buffers may be reused, refilled or freed.  Announced frames are recognised in the next call by
+ * POINTER identity and are read asynchronously until that call returns: a caller that refills the same buffers in place
+ * (ring buffer, in-place decode) must cancel the announcement first, or not announce. */
+int vors_batch_cancel_prefetch(vors_batch* b);
 int vors_batch_current_frames(const vors_batch* b, double* depth_ts, vors_pose* poses);
 int vors_batch_size(const vors_batch* b);
 /* Device time of the last track call's kernels, by stage (ms; CUDA events on the batch's stream):
@@ -241,7 +246,10 @@ int vors_candidates_dso(const uint16_t* gradients, uint32_t rows, uint32_t cols,
 int vors_gradient_norms_example(const uint8_t* img, uint32_t rows, uint32_t cols, uint32_t max_levels,
                                 uint16_t* g2_concat);
 
-/* Replaces `precompute_multires_data` (inverse_compositional.rs:105-161): keyframe precompute. */
+/* Replaces `precompute_multires_data` (inverse_compositional.rs:105-161): keyframe precompute.
+ * A keyframe handle owns device scratch (the frame pyramid slot, job descriptors) that vors_align_pass / vors_align_level /
+ * vors_align overwrite: the `const` in their signatures says that the keyframe's CANDIDATES are not modified, not that the
+ * calls are re-entrant.  One caller at a time per handle, like every other handle of this library. */
 typedef struct vors_keyframe vors_keyframe;
 int vors_keyframe_create(const vors_config* cfg, const uint16_t* depth, const uint8_t* img, uint32_t rows,
                          uint32_t cols, int layout, vors_keyframe** out);

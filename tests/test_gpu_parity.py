@@ -558,6 +558,50 @@ def test_announced_next_frames_give_identical_results(vb):
     assert np.array_equal(plain, ann)
 
 
+def test_prefetch_cancel_and_argument_checks_leave_the_batch_consistent(vb):
+    """ADVICE r01: a refilled announced buffer must be cancellable; invalid pointers are rejected before anything is queued;
+    a keyframe switch without a depth map is reported with the stream state advanced like the reference's and no switch."""
+    import ctypes as C
+    n, T = 3, 4
+    seqs = [synth.make_sequence(seed=950 + i, n_frames=T + 1, rows=60, cols=80, step_v=0.03, step_w=0.02) for i in range(n)]
+    cfg = vb.Config(nb_levels=3, **synth.scene_config_kwargs(seqs[0][0]))
+    frames = [np.ascontiguousarray(np.stack([s[1][k][0] for s in seqs])) for k in range(T + 1)]
+    depths = [np.ascontiguousarray(np.stack([s[1][k][1] for s in seqs])) for k in range(T + 1)]
+    t = lambda k: np.full(n, float(k))
+    ref = vb.BatchTracker(cfg, np.zeros(n), depths[0], np.zeros(n), frames[0])
+    ref.track(t(1), depths[1], t(1), frames[1])
+    ref.track(t(2), depths[2], t(2), frames[2])
+    # announce a buffer, cancel, refill it in place with other data, then track it: must equal the plain result
+    bt = vb.BatchTracker(cfg, np.zeros(n), depths[0], np.zeros(n), frames[0])
+    ring = frames[3].copy()  # announced with the wrong content
+    bt.track(t(1), depths[1], t(1), frames[1], next_imgs=ring)
+    bt.cancel_prefetch()
+    ring[...] = frames[2]
+    bt.track(t(2), depths[2], t(2), ring)
+    assert np.array_equal(bt.current_frames()[1], ref.current_frames()[1])
+    # a null next-image pointer: rejected, nothing changed
+    before = bt.current_frames()
+    I = 60 * 80
+    ip = (C.c_void_p * n)(*[frames[3].ctypes.data + i * I for i in range(n)])
+    dp = (C.c_void_p * n)(*[depths[3].ctypes.data + i * I * 2 for i in range(n)])
+    bad = (C.c_void_p * n)(*([frames[3].ctypes.data] + [None] * (n - 1)))
+    ts3 = t(3)
+    with pytest.raises(vb.VorsError):
+        bt.track_raw(ts3.ctypes.data, dp, ts3.ctypes.data, ip, None, None, bad)
+    after = bt.current_frames()
+    assert np.array_equal(before[0], after[0]) and np.array_equal(before[1], after[1])
+    # no depth map at a keyframe switch: error after poses / timestamps advanced, keyframe kept; the batch stays usable
+    far = [synth.make_sequence(seed=950 + i, n_frames=2, rows=60, cols=80, step_v=0.2, step_w=0.1)[1][1][0] for i in range(n)]
+    far = np.ascontiguousarray(np.stack(far))
+    fp = (C.c_void_p * n)(*[far.ctypes.data + i * I for i in range(n)])
+    with pytest.raises(vb.VorsError) as err:
+        bt.track_raw(ts3.ctypes.data, None, ts3.ctypes.data, fp, None, None, None)
+    assert "depth map required" in str(err.value)
+    assert np.array_equal(bt.current_frames()[0], ts3)
+    status, _ = bt.track(t(4), depths[3], t(4), frames[3])
+    assert status.shape == (n,)
+
+
 @pytest.mark.parametrize("mode", [0, 1])
 def test_statistically_similar_fusion_option(vb, oracle, mode):
     """idepth_fusion = 1 (inverse_depth.rs:105-152): inverse-depth pyramid and candidate lists bit-identical to the oracle,

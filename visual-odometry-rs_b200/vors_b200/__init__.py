@@ -105,6 +105,7 @@ SIGNATURES = {
     "vors_batch_track_next": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vors_batch_track_device": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vors_batch_track_device_next": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vors_batch_cancel_prefetch": (C.c_int, [_vp]),
     "vors_batch_current_frames": (C.c_int, [_vp, _vp, _vp]),
     "vors_batch_size": (C.c_int, [_vp]),
     "vors_batch_last_timing": (C.c_int, [_vp, _P(C.c_float)]),
@@ -349,6 +350,11 @@ class BatchTracker:
                                                                  status_ptr, stats_ptr), True)
         return _check(self._lib.vors_batch_track_device(self._h, dts_ptr, depth_dev_ptr, its_ptr, img_dev_ptr, status_ptr,
                                                         stats_ptr), True)
+
+    def cancel_prefetch(self):
+        """Forget the announced next frames (and wait for their copy): the buffers may then be reused."""
+        _check(self._lib.vors_batch_cancel_prefetch(self._h))
+        self._announced = None
 
     def current_frames(self):
         ts = np.zeros(self.n, np.float64)
