@@ -155,10 +155,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ float u2f(uint32_t v) { return float(v); }
 // 1/x: MUFU.RCP seed + one Newton step (2 FMAs) = correctly rounded to within 1 ulp without the slow-path range
 // checks of an IEEE division; x = 0 / inf / NaN give inf / NaN, which the inside test rejects like the reference.
+#ifndef VORS_RCP_NEWTON
+#define VORS_RCP_NEWTON 1  // 0: the raw MUFU.RCP seed (1 ulp) without the Newton step (measured: no faster, not the default)
+#endif
 __device__ __forceinline__ float rcp_approx(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+#if VORS_RCP_NEWTON
     return fmaf(r, fmaf(-x, r, 1.0f), r);
+#else
+    return r;
+#endif
 }
 
 __device__ __forceinline__ unsigned long long global_timer_ns() {
