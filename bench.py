@@ -259,11 +259,16 @@ def run_ours(args):
         return vb.BatchTracker(vcfg, ts[0], depth_h[0].numpy(), ts[0], gray_h[0].numpy(), layout=vb.ROW_MAJOR)
 
     def barrier():
+        # (collectives are enqueued in the same order on every rank: the helper thread's exchange first)
+        if pending_x[0] is not None:
+            pending_x[0].result()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
+        if pending_x[0] is not None:
+            pending_x[0].result()
         if world > 1:
             t = torch.tensor([x], dtype=torch.float64, device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -48,6 +48,28 @@ def _worker(rank, world, port, q):
     assert pg.in_flight() == 0
     assert np.array_equal(a, full), "PoseGatherer differs from gather_poses"
     assert np.array_equal(b[:, :7], full[:, :7] + 1.0) and np.array_equal(b[:, 7], full[:, 7])
+    # bench.py's pattern: the exchange is submitted from a helper thread while the main thread works; every main-thread
+    # collective first waits for the pending exchange, so that all ranks enqueue collectives in the same order
+    import concurrent.futures as cf
+    pool = cf.ThreadPoolExecutor(max_workers=1)
+    pg2 = shard.PoseGatherer(N_STREAMS, device="cpu", depth=2)
+    pending = None
+    got = []
+    def work(p, st):
+        if pg2.in_flight() == pg2.depth:
+            got.append(pg2.collect())
+        pg2.submit(p, st)
+    for k in range(5):
+        if pending is not None:
+            pending.result()
+        pending = pool.submit(work, local[:, :7] + float(k), local[:, 7].copy())
+        if k == 2:  # a main-thread collective in the middle of the loop (bench.py: the barrier before the timed region)
+            pending.result()
+            dist.barrier()
+    pending.result()
+    while pg2.in_flight():
+        got.append(pg2.collect())
+    assert len(got) == 5 and all(np.array_equal(g[:, :7], full[:, :7] + float(k)) for k, g in enumerate(got))
     q.put((rank, full))
     dist.barrier()
     dist.destroy_process_group()
