@@ -4,7 +4,6 @@
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest.log 2>&1; tail -3 gpurun_out/r02_pytest.log
 python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_c2_1gpu.json 2> gpurun_out/r02_bench_c2_1gpu.err; echo "c2 rc=$?"
-python bench.py > gpurun_out/r02_bench_c2_1gpu_default40.json 2> /dev/null; echo "c2 default rc=$?"
 for c in 1 3 4 5; do
   python bench.py --config $c --steps 20 --warmup 5 > gpurun_out/r02_bench_c${c}_1gpu.json 2> gpurun_out/r02_bench_c${c}_1gpu.err; echo "c$c rc=$?"
 done
