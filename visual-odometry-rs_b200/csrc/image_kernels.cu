@@ -111,6 +111,34 @@ __global__ void __launch_bounds__(256) k_pyramid_fused(const Geom g, int l_first
 // 1-px border 0.  Level l >= 1: bloc_x / bloc_y of the level l-1 image (gradient.rs:74-93).
 // g2 = (gx*gx + gy*gy) as u16 (gradient.rs:38-44).
 // `scharr` (extension, vors_config.gradient_operator = 1): 3x3 Scharr / 32 on every level's own image instead.
+// The (gx, gy) pair of pixel (x, y) of level l as the gradient slab stores it: gx | gy << 16, both i16.
+__device__ __forceinline__ uint32_t grad_pair_at(const Geom& g, const uint8_t* __restrict__ pyr, int scharr, int l, int x, int y, int* g2 = nullptr) {
+    const int R = g.rows[l], C = g.cols[l];
+    int gx = 0, gy = 0;
+    if (scharr) {
+        if (x > 0 && x < C - 1 && y > 0 && y < R - 1) {
+            const uint8_t* p = pyr + g.off[l] + size_t(x) * R + y;  // p[dc * R + dr]
+            const int tl = p[-R - 1], ml = p[-R], bl = p[-R + 1], tc = p[-1], bc = p[1], tr = p[R - 1], mr = p[R], br = p[R + 1];
+            gx = (3 * (tr - tl) + 10 * (mr - ml) + 3 * (br - bl)) / 32;
+            gy = (3 * (bl - tl) + 10 * (bc - tc) + 3 * (br - tr)) / 32;
+        }
+    } else if (l == 0) {
+        if (x > 0 && x < C - 1 && y > 0 && y < R - 1) {
+            const uint8_t* p = pyr + size_t(x) * R + y;
+            gx = (int(p[R]) - int(p[-R])) / 2;  // right - left, C++ `/` truncates like Rust
+            gy = (int(p[1]) - int(p[-1])) / 2;  // bottom - top
+        }
+    } else {
+        const int Rin = g.rows[l - 1];
+        const uint8_t* p = pyr + g.off[l - 1] + size_t(2 * x) * Rin + 2 * y;
+        const int a = p[0], b = p[1], c = p[Rin], d = p[Rin + 1];
+        gx = (c + d - a - b) / 2;
+        gy = (b - a + d - c) / 2;
+    }
+    if (g2) *g2 = gx * gx + gy * gy;
+    return (uint32_t(gx) & 0xFFFFu) | (uint32_t(gy) << 16);
+}
+
 __global__ void k_gradients(const Geom g, int scharr, const uint8_t* __restrict__ pyr_slab, uint32_t* __restrict__ grad_slab,
                             uint16_t* __restrict__ g2_slab, const int* __restrict__ items) {
     const size_t base = size_t(item_of(items, blockIdx.y)) * g.pix_stride;
@@ -121,31 +149,12 @@ __global__ void k_gradients(const Geom g, int scharr, const uint8_t* __restrict_
         for (int k = 1; k < kMaxLevels; ++k)
             if (k < g.L && i >= g.off[k]) l = k;
         const int o = i - g.off[l];
-        const int R = g.rows[l], C = g.cols[l];
+        const int R = g.rows[l];
         const int x = o / R, y = o - x * R;
-        int gx = 0, gy = 0;
-        if (scharr) {
-            if (x > 0 && x < C - 1 && y > 0 && y < R - 1) {
-                const uint8_t* p = pyr + g.off[l] + size_t(x) * R + y;  // p[dc * R + dr]
-                const int tl = p[-R - 1], ml = p[-R], bl = p[-R + 1], tc = p[-1], bc = p[1], tr = p[R - 1], mr = p[R], br = p[R + 1];
-                gx = (3 * (tr - tl) + 10 * (mr - ml) + 3 * (br - bl)) / 32;
-                gy = (3 * (bl - tl) + 10 * (bc - tc) + 3 * (br - tr)) / 32;
-            }
-        } else if (l == 0) {
-            if (x > 0 && x < C - 1 && y > 0 && y < R - 1) {
-                const uint8_t* p = pyr + size_t(x) * R + y;
-                gx = (int(p[R]) - int(p[-R])) / 2;  // right - left, C++ `/` truncates like Rust
-                gy = (int(p[1]) - int(p[-1])) / 2;  // bottom - top
-            }
-        } else {
-            const int Rin = g.rows[l - 1];
-            const uint8_t* p = pyr + g.off[l - 1] + size_t(2 * x) * Rin + 2 * y;
-            const int a = p[0], b = p[1], c = p[Rin], d = p[Rin + 1];
-            gx = (c + d - a - b) / 2;
-            gy = (b - a + d - c) / 2;
-        }
-        if (grad_slab) grad_slab[base + i] = (uint32_t(gx) & 0xFFFFu) | (uint32_t(gy) << 16);
-        if (g2_slab) g2_slab[base + i] = uint16_t(gx * gx + gy * gy);
+        int g2;
+        const uint32_t pair = grad_pair_at(g, pyr, scharr, l, x, y, &g2);
+        if (grad_slab) grad_slab[base + i] = pair;
+        if (g2_slab) g2_slab[base + i] = uint16_t(g2);
     }
 }
 
@@ -418,30 +427,36 @@ namespace {
 // Sum over ALL candidates of a level of J J^T (21 unique entries), once per keyframe.  The align kernel then
 // only accumulates J J^T for the candidates that fall OUTSIDE the frame in a pass and forms
 // H = H_total - H_outside (compute_eval_data's `hessian += hes`, lm_optimizer.rs:100, over the inside set).
-// Products are rounded in f32 exactly like the align kernel's, summed in f64 in a fixed order (one CTA per
-// (level, stream), strided assignment, shuffle + shared-memory tree) -> deterministic.
-__global__ void __launch_bounds__(512) k_h_total(const Geom g, const LevelIntrinsics li, const uint32_t* __restrict__ pts_slab,
-                                                 const int* __restrict__ n_points, double* __restrict__ h_total,
-                                                 const int* __restrict__ items) {
+// Products are rounded in f32 exactly like the align kernel's and summed in f64 in a fixed order -> deterministic.
+// Two steps, so that a 300 k-candidate level is not one CTA's job: partial sums per CHUNK of a level (one CTA each: strided
+// assignment, shuffle + shared-memory tree), then k_h_total_finish adds a level's chunks in order.
+constexpr int kHPart = 22;         // doubles per chunk: 21 sums + the number of valid candidates
+constexpr int kHChunkCand = 8192;  // compacted records: candidates per chunk
+constexpr int kHChunkTiles = 16;   // tiled records: tiles per chunk (6144 slots)
+struct HChunks {
+    int off[kMaxLevels + 1];  // first chunk of level l; off[l >= L] = chunks per stream
+};
+
+__device__ __forceinline__ int level_of_chunk(const Geom& g, const HChunks& hc, int chunk) {
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < kMaxLevels; ++k)
+        if (k < g.L && chunk >= hc.off[k]) l = k;
+    return l;
+}
+
+__device__ __forceinline__ void h_accumulate(const float (&J)[6], double (&acc)[21]) {
+    int t = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = a; b < 6; ++b, ++t) acc[t] += double(J[a]) * double(J[b]);  // exact in f64
+}
+
+// block sum (blockDim.x = 512) of the per-thread partials -> out[0..20], out[21] = number of valid candidates
+__device__ __forceinline__ void h_block_reduce(double (&acc)[21], int valid, double* __restrict__ out) {
     __shared__ double part[16][21];
-    const int it = item_of(items, blockIdx.y), l = blockIdx.x;
-    const uint32_t* lvl = pts_slab + 3 * (size_t(it) * g.pt_total + g.pt_off[l]);
-    const int n = n_points[it * kMaxLevels + l];
-    const Intrinsics k = li.k[l];
-    double acc[21];
-#pragma unroll
-    for (int c = 0; c < 21; ++c) acc[c] = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint32_t p = lvl[pt_word(i, 0)], gr = lvl[pt_word(i, 2)];
-        float J[6];
-        jacobian_at<true>(rec_gx(gr), rec_gy(gr), float(rec_x(p)), float(rec_y(p)),
-                          __uint_as_float(lvl[pt_word(i, 1)]), k, J);
-        int t = 0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a)
-#pragma unroll
-            for (int b = a; b < 6; ++b, ++t) acc[t] += double(J[a]) * double(J[b]);  // exact in f64
-    }
+    __shared__ int cnt[16];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int c = 0; c < 21; ++c) {
@@ -450,11 +465,61 @@ __global__ void __launch_bounds__(512) k_h_total(const Geom g, const LevelIntrin
         for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
         if (lane == 0) part[w][c] = v;
     }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, d);
+    if (lane == 0) cnt[w] = valid;
     __syncthreads();
     if (threadIdx.x < 21) {
         double s = 0.0;
         for (int ww = 0; ww < int(blockDim.x >> 5); ++ww) s += part[ww][threadIdx.x];
-        h_total[(size_t(it) * kMaxLevels + l) * kHStride + threadIdx.x] = s;
+        out[threadIdx.x] = s;
+    }
+    if (threadIdx.x == 32) {
+        int s = 0;
+        for (int ww = 0; ww < int(blockDim.x >> 5); ++ww) s += cnt[ww];
+        out[21] = double(s);
+    }
+}
+
+__global__ void __launch_bounds__(512) k_h_total(const Geom g, const LevelIntrinsics li, const HChunks hc,
+                                                 const uint32_t* __restrict__ pts_slab, const int* __restrict__ n_points,
+                                                 double* __restrict__ part, const int* __restrict__ items) {
+    const int it = item_of(items, blockIdx.y), l = level_of_chunk(g, hc, blockIdx.x);
+    const int n = n_points[it * kMaxLevels + l];
+    const int i0 = (int(blockIdx.x) - hc.off[l]) * kHChunkCand, i1 = min(n, i0 + kHChunkCand);
+    if (i0 >= n) return;  // (the whole CTA) chunks beyond the level's candidates: k_h_total_finish does not read them
+    const uint32_t* lvl = pts_slab + 3 * (size_t(it) * g.pt_total + g.pt_off[l]);
+    const Intrinsics k = li.k[l];
+    double acc[21];
+#pragma unroll
+    for (int c = 0; c < 21; ++c) acc[c] = 0.0;
+    int valid = 0;
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const uint32_t p = lvl[pt_word(i, 0)], gr = lvl[pt_word(i, 2)];
+        float J[6];
+        jacobian_at<true>(rec_gx(gr), rec_gy(gr), float(rec_x(p)), float(rec_y(p)),
+                          __uint_as_float(lvl[pt_word(i, 1)]), k, J);
+        h_accumulate(J, acc);
+        ++valid;
+    }
+    h_block_reduce(acc, valid, part + (size_t(blockIdx.y) * hc.off[kMaxLevels] + blockIdx.x) * kHPart);
+}
+
+// `chunk_cand` > 0: compacted records, a level's chunks in use follow from its candidate count; 0: tiled records, every
+// chunk was written and the valid slots they counted become the level's n_points.
+__global__ void k_h_total_finish(const Geom g, const HChunks hc, int chunk_cand, const double* __restrict__ part,
+                                 int* __restrict__ n_points, double* __restrict__ h_total, const int* __restrict__ items) {
+    const int it = item_of(items, blockIdx.y), l = blockIdx.x;
+    int used = hc.off[l + 1] - hc.off[l];
+    if (chunk_cand) used = min(used, (n_points[it * kMaxLevels + l] + chunk_cand - 1) / chunk_cand);
+    const double* p = part + (size_t(blockIdx.y) * hc.off[kMaxLevels] + hc.off[l]) * kHPart;
+    if (threadIdx.x < kHPart) {
+        double s = 0.0;
+        for (int c = 0; c < used; ++c) s += p[size_t(c) * kHPart + threadIdx.x];
+        if (threadIdx.x < 21)
+            h_total[(size_t(it) * kMaxLevels + l) * kHStride + threadIdx.x] = s;
+        else if (!chunk_cand)
+            n_points[it * kMaxLevels + l] = int(s);
     }
 }
 
@@ -492,8 +557,8 @@ __global__ void k_lie(int op, const float* __restrict__ in, float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Tiled dense records (vors_device.cuh): one CTA of 256 threads writes one tile = one 2560-byte ring stage of the align
-// kernel, slot (j, lane) = pixel (x = 8 tx + j, y = 32 ty + lane) of the tile's level.  No compaction: a pixel outside the
+// Tiled dense records (vors_device.cuh): one CTA of 384 threads writes one tile = one 3840-byte ring stage of the align
+// kernel, slot (j, lane) = pixel (x = 12 tx + j, y = 32 ty + lane) of the tile's level.  No compaction: a pixel outside the
 // image or without a known inverse depth gets a NaN inverse depth (extract_z, inverse_compositional.rs:260-279, keeps
 // exactly the pixels whose inverse depth is known; here they keep their place and the others are marked).
 __device__ __forceinline__ int level_of_tile(const Geom& g, int tile) {
@@ -504,10 +569,11 @@ __device__ __forceinline__ int level_of_tile(const Geom& g, int tile) {
     return l;
 }
 
-__global__ void __launch_bounds__(kTileSlots) k_tile_records(const Geom g, const float* __restrict__ idepth_slab,
+__global__ void __launch_bounds__(kTileSlots) k_tile_records(const Geom g, int scharr, const float* __restrict__ idepth_slab,
                                                              const uint8_t* __restrict__ pyr_slab,
                                                              const uint32_t* __restrict__ grad_slab, uint32_t* __restrict__ pts_slab,
                                                              const int* __restrict__ items) {
+    __shared__ __align__(16) uint32_t s_tile[kTileWords];  // the tile is assembled here and leaves with 16-byte stores
     const int it = item_of(items, blockIdx.y);
     const size_t base = size_t(it) * g.pix_stride;
     const int tile = blockIdx.x, l = level_of_tile(g, tile);
@@ -524,31 +590,34 @@ __global__ void __launch_bounds__(kTileSlots) k_tile_records(const Geom g, const
         const float d = idepth_slab[src];
         if (!isnan(d)) {
             rho = d;
-            gr = rec_pack_grad(grad_slab[src]);
+            // (no gradient slab: the Tracker's gradient recipe evaluated here, same function as k_gradients)
+            gr = rec_pack_grad(grad_slab ? grad_slab[src] : grad_pair_at(g, pyr_slab + base, scharr, l, x, y));
             tm = __half_as_ushort(__float2half_rn(float(pyr_slab[src])));  // 0..255: exact in f16
         }
     }
-    uint32_t* st = pts_slab + (size_t(it) * g.tile_total + tile) * kTileWords;
-    st[tile_rho_word(j, lane)] = __float_as_uint(rho);
-    st[tile_grad_word(j, lane)] = gr;
-    reinterpret_cast<unsigned short*>(st)[tile_tmpl_half(j, lane)] = tm;
+    s_tile[tile_rho_word(j, lane)] = __float_as_uint(rho);
+    s_tile[tile_grad_word(j, lane)] = gr;
+    reinterpret_cast<unsigned short*>(s_tile)[tile_tmpl_half(j, lane)] = tm;
+    __syncthreads();
+    uint4* st = reinterpret_cast<uint4*>(pts_slab + (size_t(it) * g.tile_total + tile) * kTileWords);
+    if (threadIdx.x < kTileWords / 4) st[threadIdx.x] = reinterpret_cast<const uint4*>(s_tile)[threadIdx.x];
 }
+static_assert(kTileWords % 4 == 0 && kTileWords / 4 <= kTileSlots, "one 16-byte store per thread moves a tile");
 
-// Row K for tiled records: sum of J J^T over the level's valid slots (f64, fixed order) and their count (-> n_points).
-__global__ void __launch_bounds__(512) k_h_total_tiled(const Geom g, const LevelIntrinsics li, const uint32_t* __restrict__ pts_slab,
-                                                       int* __restrict__ n_points, double* __restrict__ h_total,
+// Row K for tiled records: partial sums of J J^T over the valid slots of a chunk of kHChunkTiles tiles and their count.
+__global__ void __launch_bounds__(512) k_h_total_tiled(const Geom g, const LevelIntrinsics li, const HChunks hc,
+                                                       const uint32_t* __restrict__ pts_slab, double* __restrict__ part,
                                                        const int* __restrict__ items) {
-    __shared__ double part[16][21];
-    __shared__ int cnt[16];
-    const int it = item_of(items, blockIdx.y), l = blockIdx.x;
+    const int it = item_of(items, blockIdx.y), l = level_of_chunk(g, hc, blockIdx.x);
+    const int tiles_y = g.tiles_y[l], tiles_l = tiles_y * g.tiles_x[l];
+    const int t0 = (int(blockIdx.x) - hc.off[l]) * kHChunkTiles, t1 = min(tiles_l, t0 + kHChunkTiles);
     const uint32_t* lvl = pts_slab + (size_t(it) * g.tile_total + g.tile_off[l]) * kTileWords;
-    const int n_slots = g.tiles_y[l] * g.tiles_x[l] * kTileSlots, tiles_y = g.tiles_y[l];
     const Intrinsics k = li.k[l];
     double acc[21];
 #pragma unroll
     for (int c = 0; c < 21; ++c) acc[c] = 0.0;
     int valid = 0;
-    for (int i = threadIdx.x; i < n_slots; i += blockDim.x) {
+    for (int i = t0 * kTileSlots + threadIdx.x; i < t1 * kTileSlots; i += blockDim.x) {
         const int st = i / kTileSlots, j = (i / kTileRows) % kTileCols, ln = i % kTileRows;
         const uint32_t* w = lvl + size_t(st) * kTileWords;
         const float rho = __uint_as_float(w[tile_rho_word(j, ln)]);
@@ -558,58 +627,62 @@ __global__ void __launch_bounds__(512) k_h_total_tiled(const Geom g, const Level
         const uint32_t gr = w[tile_grad_word(j, ln)];
         float J[6];
         jacobian_at<true>(rec_gx(gr), rec_gy(gr), float(kTileCols * tx + j), float(kTileRows * ty + ln), rho, k, J);
-        int t = 0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a)
-#pragma unroll
-            for (int b = a; b < 6; ++b, ++t) acc[t] += double(J[a]) * double(J[b]);  // exact in f64
+        h_accumulate(J, acc);
     }
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int c = 0; c < 21; ++c) {
-        double v = acc[c];
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        if (lane == 0) part[w][c] = v;
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, d);
-    if (lane == 0) cnt[w] = valid;
-    __syncthreads();
-    if (threadIdx.x < 21) {
-        double s = 0.0;
-        for (int ww = 0; ww < int(blockDim.x >> 5); ++ww) s += part[ww][threadIdx.x];
-        h_total[(size_t(it) * kMaxLevels + l) * kHStride + threadIdx.x] = s;
-    }
-    if (threadIdx.x == 32) {
-        int s = 0;
-        for (int ww = 0; ww < int(blockDim.x >> 5); ++ww) s += cnt[ww];
-        n_points[it * kMaxLevels + l] = s;
-    }
+    h_block_reduce(acc, valid, part + (size_t(blockIdx.y) * hc.off[kMaxLevels] + blockIdx.x) * kHPart);
 }
 
 // Frame pyramids -> atlas page (vors_device.cuh): every level of every listed stream, through surface stores.
-// Texture x = image row (the fast axis of the column-major pyramid): consecutive threads write consecutive texels.
-__global__ void k_atlas_fill(const Geom g, const uint8_t* __restrict__ pyr_slab, const AtlasPages pages, const int* __restrict__ items,
-                             int first) {
+// Texture x = image row (the fast axis of the column-major pyramid).  A thread moves a QUAD = four consecutive rows of one
+// column: one 4-byte load and one 4-byte surface store (8-byte for f16 texels) where both are aligned - cells start at
+// multiples of four texels - else texel by texel (last rows of a level whose height is not a multiple of four, odd slabs).
+struct AtlasQuads {
+    int off[kMaxLevels + 1];  // first quad of level l; off[l >= L] = quads per stream
+};
+
+__device__ __forceinline__ void atlas_store1(const AtlasPages& pages, cudaSurfaceObject_t surf, uint8_t v, int tx, int ty) {
+    if (pages.f16)
+        surf2Dwrite<unsigned short>(__half_as_ushort(__float2half_rn(float(v))), surf, tx * 2, ty);
+    else
+        surf2Dwrite<unsigned char>(v, surf, tx, ty);
+}
+
+__global__ void k_atlas_fill(const Geom g, const AtlasQuads aq, const uint8_t* __restrict__ pyr_slab, const AtlasPages pages,
+                             const int* __restrict__ items, int first) {
     // stream `it`; its slab sits at index items[j] of pyr_slab, or at index j when pyr_slab already points at stream `first`
     const int it = items ? items[blockIdx.y] : first + int(blockIdx.y);
     const uint8_t* pyr = pyr_slab + size_t(items ? items[blockIdx.y] : int(blockIdx.y)) * g.pix_stride;
     const int page = it / g.per_page, cell = it - page * g.per_page;
     const int ox = (cell % g.per_row) * g.cell_w, oy = (cell / g.per_row) * g.cell_h;
     const cudaSurfaceObject_t surf = pages.surf[page];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.pix_total; i += gridDim.x * blockDim.x) {
-        int l = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < aq.off[kMaxLevels]; i += gridDim.x * blockDim.x) {
+        // (the level's constants by unrolled selects: dynamic indexing would copy the parameter structs to local memory)
+        int q0 = 0, R = g.rows[0], p0 = 0, ly = 0;
 #pragma unroll
         for (int k = 1; k < kMaxLevels; ++k)
-            if (k < g.L && i >= g.off[k]) l = k;
-        const int o = i - g.off[l];
-        const int R = g.rows[l];
-        const int x = o / R, y = o - x * R;
-        if (pages.f16)
-            surf2Dwrite<unsigned short>(__half_as_ushort(__float2half_rn(float(pyr[i]))), surf, (ox + y) * 2, oy + g.lvl_y[l] + x);
-        else
-            surf2Dwrite<unsigned char>(pyr[i], surf, ox + y, oy + g.lvl_y[l] + x);
+            if (k < g.L && i >= aq.off[k]) {
+                q0 = aq.off[k];
+                R = g.rows[k];
+                p0 = g.off[k];
+                ly = g.lvl_y[k];
+            }
+        const int o = i - q0, Q = (R + 3) >> 2;
+        const int x = o / Q, y = (o - x * Q) * 4;
+        const uint8_t* src = pyr + p0 + size_t(x) * R + y;
+        const int tx = ox + y, ty = oy + ly + x;
+        const int nv = min(4, R - y);
+        if (nv == 4 && ((reinterpret_cast<uintptr_t>(src) | uintptr_t(tx)) & 3u) == 0) {
+            const uchar4 v = *reinterpret_cast<const uchar4*>(src);
+            if (pages.f16) {
+                const ushort4 h = make_ushort4(__half_as_ushort(__float2half_rn(float(v.x))), __half_as_ushort(__float2half_rn(float(v.y))),
+                                               __half_as_ushort(__float2half_rn(float(v.z))), __half_as_ushort(__float2half_rn(float(v.w))));
+                surf2Dwrite<ushort4>(h, surf, tx * 2, ty);
+            } else {
+                surf2Dwrite<uchar4>(v, surf, tx, ty);
+            }
+        } else {
+            for (int k = 0; k < nv; ++k) atlas_store1(pages, surf, src[k], tx + k, ty);
+        }
     }
 }
 
@@ -689,27 +762,54 @@ void launch_compact(Launcher& L, const Geom& g, const float* idepth_slab, const 
     k_compact_scatter<<<gridb, kCompactBlock, 0, L.stream>>>(g, idepth_slab, pyr_slab, grad_slab, blk_count, pts_slab, items);
     L.launches += 3;
 }
-void launch_h_total(Launcher& L, const Geom& g, const Intrinsics* intr, const uint32_t* pts_slab, const int* n_points,
-                    double* h_total, const int* items, int m) {
-    LevelIntrinsics li;
-    for (int l = 0; l < kMaxLevels; ++l) li.k[l] = intr[l < g.L ? l : g.L - 1];
-    dim3 grid(g.L, m);
-    k_h_total<<<grid, 512, 0, L.stream>>>(g, li, pts_slab, n_points, h_total, items);
-    ++L.launches;
+namespace {
+HChunks h_chunks(const Geom& g, bool tiled) {
+    HChunks hc;
+    int off = 0;
+    for (int l = 0; l <= kMaxLevels; ++l) {
+        hc.off[l] = off;
+        if (l < g.L)
+            off += tiled ? (g.tiles_y[l] * g.tiles_x[l] + kHChunkTiles - 1) / kHChunkTiles
+                         : (g.rows[l] * g.cols[l] + kHChunkCand - 1) / kHChunkCand;
+    }
+    return hc;
 }
-void launch_tile_records(Launcher& L, const Geom& g, const Intrinsics* intr, const float* idepth_slab, const uint8_t* pyr_slab,
-                          const uint32_t* grad_slab, int* n_points, uint32_t* pts_slab, double* h_total, const int* items, int m) {
-    dim3 grid(g.tile_total, m);
-    k_tile_records<<<grid, kTileSlots, 0, L.stream>>>(g, idepth_slab, pyr_slab, grad_slab, pts_slab, items);
+LevelIntrinsics level_intrinsics(const Geom& g, const Intrinsics* intr) {
     LevelIntrinsics li;
     for (int l = 0; l < kMaxLevels; ++l) li.k[l] = intr[l < g.L ? l : g.L - 1];
-    dim3 gridh(g.L, m);
-    k_h_total_tiled<<<gridh, 512, 0, L.stream>>>(g, li, pts_slab, n_points, h_total, items);
+    return li;
+}
+}  // namespace
+size_t h_total_scratch_doubles(const Geom& g, bool tiled) { return size_t(h_chunks(g, tiled).off[kMaxLevels]) * kHPart; }
+
+void launch_h_total(Launcher& L, const Geom& g, const Intrinsics* intr, const uint32_t* pts_slab, int* n_points, double* h_part,
+                    double* h_total, const int* items, int m) {
+    const HChunks hc = h_chunks(g, false);
+    dim3 grid(hc.off[kMaxLevels], m), gridf(g.L, m);
+    k_h_total<<<grid, 512, 0, L.stream>>>(g, level_intrinsics(g, intr), hc, pts_slab, n_points, h_part, items);
+    k_h_total_finish<<<gridf, 32, 0, L.stream>>>(g, hc, kHChunkCand, h_part, n_points, h_total, items);
     L.launches += 2;
 }
+void launch_tile_records(Launcher& L, const Geom& g, const Intrinsics* intr, int scharr, const float* idepth_slab, const uint8_t* pyr_slab,
+                         const uint32_t* grad_slab, int* n_points, uint32_t* pts_slab, double* h_part, double* h_total, const int* items,
+                         int m) {
+    dim3 grid(g.tile_total, m);
+    k_tile_records<<<grid, kTileSlots, 0, L.stream>>>(g, scharr, idepth_slab, pyr_slab, grad_slab, pts_slab, items);
+    const HChunks hc = h_chunks(g, true);
+    dim3 gridh(hc.off[kMaxLevels], m), gridf(g.L, m);
+    k_h_total_tiled<<<gridh, 512, 0, L.stream>>>(g, level_intrinsics(g, intr), hc, pts_slab, h_part, items);
+    k_h_total_finish<<<gridf, 32, 0, L.stream>>>(g, hc, 0, h_part, n_points, h_total, items);
+    L.launches += 3;
+}
 void launch_atlas_fill(Launcher& L, const Geom& g, const uint8_t* pyr_slab, const AtlasPages& pages, const int* items, int m, int first) {
-    dim3 grid(grid_for(g.pix_total, 256, std::max(64, 148 * 8 / std::max(m, 1))), m);  // a single stream still fills the device
-    k_atlas_fill<<<grid, 256, 0, L.stream>>>(g, pyr_slab, pages, items, first);
+    AtlasQuads aq;
+    int off = 0;
+    for (int l = 0; l <= kMaxLevels; ++l) {
+        aq.off[l] = off;
+        if (l < g.L) off += ((g.rows[l] + 3) / 4) * g.cols[l];
+    }
+    dim3 grid(grid_for(off, 256, std::max(64, 148 * 8 / std::max(m, 1))), m);  // a single stream still fills the device
+    k_atlas_fill<<<grid, 256, 0, L.stream>>>(g, aq, pyr_slab, pages, items, first);
     ++L.launches;
 }
 void launch_jacobians(Launcher& L, const uint32_t* pts_level, int n, Intrinsics k, float* out6) {

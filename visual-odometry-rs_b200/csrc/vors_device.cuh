@@ -23,8 +23,9 @@
 //     loop, whose unrolled body of six words still fits the instruction cache.)
 //   * the frame pyramids the align kernel SAMPLES live in gather-enabled 2D CUDA arrays ("atlas pages", u8 texels read as
 //     texel / 255, or f16 with -DVORS_TEX_F16=1): texture x = image y.  Stream s, level l occupies the cell at
-//     (ox, oy) = ((s % per_row) * cell_w, (s / per_row) * cell_h + lvl_y[l]) with cell_w = rows_0 + 2, lvl_y[l] = sum_{k<l}
+//     (ox, oy) = ((s % per_row) * cell_w, (s / per_row) * cell_h + lvl_y[l]) with cell_w = rows_0 + 2 rounded up to a multiple of 4, lvl_y[l] = sum_{k<l}
 //     (cols_k + 2): the two texels after every level's last row / column are never written (zero) and serve as the zero page.
+//     k_atlas_fill writes four texels per surface store, which is why cells start at multiples of four texels.
 //     One tld4 returns the 2x2 footprint of a warped candidate.  The linear pyramids stay: keyframe build and the exact
 //     re-evaluation of boundary-band candidates read them.
 #pragma once
@@ -83,7 +84,7 @@ struct Geom {
     int tile_off[kMaxLevels];    // first tile (= stage) of level l inside a stream's tiled record slab
     int tile_total;              // tiles per stream
     // texture atlas cell of one stream
-    int cell_w, cell_h;          // rows_0 + 2, sum (cols_l + 2)
+    int cell_w, cell_h;          // rows_0 + 2 rounded up to a multiple of 4, sum (cols_l + 2)
     int lvl_y[kMaxLevels];       // texel row of level l inside the cell
     int per_row, per_page;       // cells per atlas row / per atlas page
 };
@@ -235,11 +236,15 @@ void launch_idepth(Launcher& L, const Geom& g, const uint16_t* depth_slab, size_
                    int m);
 void launch_compact(Launcher& L, const Geom& g, const float* idepth_slab, const uint8_t* pyr_slab, const uint32_t* grad_slab,
                     int* blk_count, int* n_points, uint32_t* pts_slab, const int* items, int m);
-void launch_h_total(Launcher& L, const Geom& g, const Intrinsics* intr, const uint32_t* pts_slab, const int* n_points,
+// `h_part`: scratch of h_total_scratch_doubles() doubles per listed stream (partial sums per chunk of a level)
+size_t h_total_scratch_doubles(const Geom& g, bool tiled);
+void launch_h_total(Launcher& L, const Geom& g, const Intrinsics* intr, const uint32_t* pts_slab, int* n_points, double* h_part,
                     double* h_total, const int* items, int m);
-// tiled dense keyframes: records + H_total + candidate counts of all levels (replaces launch_compact + launch_h_total)
-void launch_tile_records(Launcher& L, const Geom& g, const Intrinsics* intr, const float* idepth_slab, const uint8_t* pyr_slab,
-                         const uint32_t* grad_slab, int* n_points, uint32_t* pts_slab, double* h_total, const int* items, int m);
+// tiled dense keyframes: records + H_total + candidate counts of all levels (replaces launch_compact + launch_h_total);
+// grad_slab == nullptr: the gradients are computed from the pyramid on the fly (`scharr` as for launch_gradients)
+void launch_tile_records(Launcher& L, const Geom& g, const Intrinsics* intr, int scharr, const float* idepth_slab, const uint8_t* pyr_slab,
+                         const uint32_t* grad_slab, int* n_points, uint32_t* pts_slab, double* h_part, double* h_total, const int* items,
+                         int m);
 // linear frame pyramids of m streams (items, or first .. first + m - 1 when items == nullptr and pyr_slab points at stream
 // `first`'s slab) -> their cells of the atlas pages
 constexpr int kMaxAtlasPages = 8;
