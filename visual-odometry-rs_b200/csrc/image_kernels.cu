@@ -432,7 +432,7 @@ namespace {
 // assignment, shuffle + shared-memory tree), then k_h_total_finish adds a level's chunks in order.
 constexpr int kHPart = 22;         // doubles per chunk: 21 sums + the number of valid candidates
 constexpr int kHChunkCand = 8192;  // compacted records: candidates per chunk
-constexpr int kHChunkTiles = 16;   // tiled records: tiles per chunk (6144 slots)
+constexpr int kHChunkTiles = 128;  // tiled records: tiles per chunk (8 tiles per warp of the 512-thread CTA)
 struct HChunks {
     int off[kMaxLevels + 1];  // first chunk of level l; off[l >= L] = chunks per stream
 };
@@ -587,12 +587,15 @@ __global__ void __launch_bounds__(kTileSlots) k_tile_records(const Geom g, int s
     unsigned short tm = 0;
     if (x < C && y < R) {
         const size_t src = base + g.off[l] + size_t(x) * R + y;
+        // every load is issued before the first one is looked at (one DRAM latency per tile, not two)
         const float d = idepth_slab[src];
+        // (no gradient slab: the Tracker's gradient recipe evaluated here, same function as k_gradients)
+        const uint32_t pair = grad_slab ? grad_slab[src] : grad_pair_at(g, pyr_slab + base, scharr, l, x, y);
+        const uint8_t t8 = pyr_slab[src];
         if (!isnan(d)) {
             rho = d;
-            // (no gradient slab: the Tracker's gradient recipe evaluated here, same function as k_gradients)
-            gr = rec_pack_grad(grad_slab ? grad_slab[src] : grad_pair_at(g, pyr_slab + base, scharr, l, x, y));
-            tm = __half_as_ushort(__float2half_rn(float(pyr_slab[src])));  // 0..255: exact in f16
+            gr = rec_pack_grad(pair);
+            tm = __half_as_ushort(__float2half_rn(float(t8)));  // 0..255: exact in f16
         }
     }
     s_tile[tile_rho_word(j, lane)] = __float_as_uint(rho);
@@ -605,6 +608,7 @@ __global__ void __launch_bounds__(kTileSlots) k_tile_records(const Geom g, int s
 static_assert(kTileWords % 4 == 0 && kTileWords / 4 <= kTileSlots, "one 16-byte store per thread moves a tile");
 
 // Row K for tiled records: partial sums of J J^T over the valid slots of a chunk of kHChunkTiles tiles and their count.
+static_assert(kTileHalfCols % 2 == 0 && (kTileRows * kTileHalfCols) % 2 == 0 && kTileSlots % 2 == 0, "8-byte loads of a lane's half row");
 __global__ void __launch_bounds__(512) k_h_total_tiled(const Geom g, const LevelIntrinsics li, const HChunks hc,
                                                        const uint32_t* __restrict__ pts_slab, double* __restrict__ part,
                                                        const int* __restrict__ items) {
@@ -613,21 +617,36 @@ __global__ void __launch_bounds__(512) k_h_total_tiled(const Geom g, const Level
     const int t0 = (int(blockIdx.x) - hc.off[l]) * kHChunkTiles, t1 = min(tiles_l, t0 + kHChunkTiles);
     const uint32_t* lvl = pts_slab + (size_t(it) * g.tile_total + g.tile_off[l]) * kTileWords;
     const Intrinsics k = li.k[l];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double acc[21];
 #pragma unroll
     for (int c = 0; c < 21; ++c) acc[c] = 0.0;
     int valid = 0;
-    for (int i = t0 * kTileSlots + threadIdx.x; i < t1 * kTileSlots; i += blockDim.x) {
-        const int st = i / kTileSlots, j = (i / kTileRows) % kTileCols, ln = i % kTileRows;
-        const uint32_t* w = lvl + size_t(st) * kTileWords;
-        const float rho = __uint_as_float(w[tile_rho_word(j, ln)]);
-        if (isnan(rho) || rho == 0.0f) continue;
-        ++valid;
+    // a warp takes whole tiles, lane = row, the twelve columns unrolled: no per-slot index arithmetic, and the six inverse
+    // depths / gradient pairs of a lane's half row arrive with three 8-byte loads each (the align kernel's access pattern)
+    for (int st = t0 + warp; st < t1; st += int(blockDim.x >> 5)) {
         const int tx = st / tiles_y, ty = st - tx * tiles_y;
-        const uint32_t gr = w[tile_grad_word(j, ln)];
-        float J[6];
-        jacobian_at<true>(rec_gx(gr), rec_gy(gr), float(kTileCols * tx + j), float(kTileRows * ty + ln), rho, k, J);
-        h_accumulate(J, acc);
+        const uint32_t* w = lvl + size_t(st) * kTileWords;
+        const float y = float(kTileRows * ty + lane);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint2 r2[kTileHalfCols / 2], g2[kTileHalfCols / 2];
+#pragma unroll
+            for (int q = 0; q < kTileHalfCols / 2; ++q) {
+                r2[q] = *reinterpret_cast<const uint2*>(w + tile_rho_word(kTileHalfCols * h + 2 * q, lane));
+                g2[q] = *reinterpret_cast<const uint2*>(w + tile_grad_word(kTileHalfCols * h + 2 * q, lane));
+            }
+#pragma unroll
+            for (int c = 0; c < kTileHalfCols; ++c) {
+                const float rho = __uint_as_float((c & 1) ? r2[c >> 1].y : r2[c >> 1].x);
+                const uint32_t gr = (c & 1) ? g2[c >> 1].y : g2[c >> 1].x;
+                if (isnan(rho) || rho == 0.0f) continue;
+                ++valid;
+                float J[6];
+                jacobian_at<true>(rec_gx(gr), rec_gy(gr), float(kTileCols * tx + kTileHalfCols * h + c), y, rho, k, J);
+                h_accumulate(J, acc);
+            }
+        }
     }
     h_block_reduce(acc, valid, part + (size_t(blockIdx.y) * hc.off[kMaxLevels] + blockIdx.x) * kHPart);
 }
