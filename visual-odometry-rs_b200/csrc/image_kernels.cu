@@ -427,7 +427,8 @@ namespace {
 // Sum over ALL candidates of a level of J J^T (21 unique entries), once per keyframe.  The align kernel then
 // only accumulates J J^T for the candidates that fall OUTSIDE the frame in a pass and forms
 // H = H_total - H_outside (compute_eval_data's `hessian += hes`, lm_optimizer.rs:100, over the inside set).
-// Products are rounded in f32 exactly like the align kernel's and summed in f64 in a fixed order -> deterministic.
+// J is the reference's, bit for bit (jacobian_exact); its products are exact in f64 and summed in f64 in a fixed order ->
+// deterministic, and independent of how the compiler contracts the surrounding code.
 // Two steps, so that a 300 k-candidate level is not one CTA's job: partial sums per CHUNK of a level (one CTA each: strided
 // assignment, shuffle + shared-memory tree), then k_h_total_finish adds a level's chunks in order.
 constexpr int kHPart = 22;         // doubles per chunk: 21 sums + the number of valid candidates
@@ -497,8 +498,7 @@ __global__ void __launch_bounds__(512) k_h_total(const Geom g, const LevelIntrin
     for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
         const uint32_t p = lvl[pt_word(i, 0)], gr = lvl[pt_word(i, 2)];
         float J[6];
-        jacobian_at<true>(rec_gx(gr), rec_gy(gr), float(rec_x(p)), float(rec_y(p)),
-                          __uint_as_float(lvl[pt_word(i, 1)]), k, J);
+        jacobian_exact(rec_gx(gr), rec_gy(gr), float(rec_x(p)), float(rec_y(p)), __uint_as_float(lvl[pt_word(i, 1)]), k, J);
         h_accumulate(J, acc);
         ++valid;
     }
@@ -557,7 +557,7 @@ __global__ void k_lie(int op, const float* __restrict__ in, float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Tiled dense records (vors_device.cuh): one CTA of 384 threads writes one tile = one 3840-byte ring stage of the align
+// Tiled dense records (vors_device.cuh): one warp writes one tile = one 3840-byte ring stage of the align
 // kernel, slot (j, lane) = pixel (x = 12 tx + j, y = 32 ty + lane) of the tile's level.  No compaction: a pixel outside the
 // image or without a known inverse depth gets a NaN inverse depth (extract_z, inverse_compositional.rs:260-279, keeps
 // exactly the pixels whose inverse depth is known; here they keep their place and the others are marked).
@@ -569,43 +569,52 @@ __device__ __forceinline__ int level_of_tile(const Geom& g, int tile) {
     return l;
 }
 
-__global__ void __launch_bounds__(kTileSlots) k_tile_records(const Geom g, int scharr, const float* __restrict__ idepth_slab,
-                                                             const uint8_t* __restrict__ pyr_slab,
-                                                             const uint32_t* __restrict__ grad_slab, uint32_t* __restrict__ pts_slab,
-                                                             const int* __restrict__ items) {
-    __shared__ __align__(16) uint32_t s_tile[kTileWords];  // the tile is assembled here and leaves with 16-byte stores
+constexpr int kTileCtaWarps = 8;  // tiles per CTA of k_tile_records: a warp per tile
+__global__ void __launch_bounds__(kTileCtaWarps * 32) k_tile_records(const Geom g, int scharr, const float* __restrict__ idepth_slab,
+                                                                     const uint8_t* __restrict__ pyr_slab,
+                                                                     const uint32_t* __restrict__ grad_slab,
+                                                                     uint32_t* __restrict__ pts_slab, const int* __restrict__ items) {
+    // a warp assembles its tile here (lane = row, the twelve columns unrolled: the tile's index arithmetic is paid once per
+    // lane and all of a lane's loads are in flight together); the tile then leaves with 16-byte stores
+    __shared__ __align__(16) uint32_t s_tile[kTileCtaWarps][kTileWords];
     const int it = item_of(items, blockIdx.y);
     const size_t base = size_t(it) * g.pix_stride;
-    const int tile = blockIdx.x, l = level_of_tile(g, tile);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * kTileCtaWarps + warp;
+    if (tile >= g.tile_total) return;  // (a whole warp; nothing below synchronises the block)
+    const int l = level_of_tile(g, tile);
     const int t = tile - g.tile_off[l], tx = t / g.tiles_y[l], ty = t - tx * g.tiles_y[l];
-    const int j = threadIdx.x / kTileRows, lane = threadIdx.x % kTileRows;
-    const int x = kTileCols * tx + j, y = kTileRows * ty + lane;
     const int R = g.rows[l], C = g.cols[l];
-    // rows below the image: zero inverse depth (the align kernel's dead lanes); columns beyond it and pixels without depth: NaN
-    float rho = y < R ? __int_as_float(0x7fc00000) : 0.0f;
-    uint32_t gr = 0u;
-    unsigned short tm = 0;
-    if (x < C && y < R) {
-        const size_t src = base + g.off[l] + size_t(x) * R + y;
-        // every load is issued before the first one is looked at (one DRAM latency per tile, not two)
-        const float d = idepth_slab[src];
-        // (no gradient slab: the Tracker's gradient recipe evaluated here, same function as k_gradients)
-        const uint32_t pair = grad_slab ? grad_slab[src] : grad_pair_at(g, pyr_slab + base, scharr, l, x, y);
-        const uint8_t t8 = pyr_slab[src];
-        if (!isnan(d)) {
-            rho = d;
-            gr = rec_pack_grad(pair);
-            tm = __half_as_ushort(__float2half_rn(float(t8)));  // 0..255: exact in f16
+    const int y = kTileRows * ty + lane;
+    uint32_t* s = s_tile[warp];
+#pragma unroll
+    for (int j = 0; j < kTileCols; ++j) {
+        const int x = kTileCols * tx + j;
+        // rows below the image: zero inverse depth (the align kernel's dead lanes); columns beyond it and pixels without depth: NaN
+        float rho = y < R ? __int_as_float(0x7fc00000) : 0.0f;
+        uint32_t gr = 0u;
+        unsigned short tm = 0;
+        if (x < C && y < R) {
+            const size_t src = base + g.off[l] + size_t(x) * R + y;
+            const float d = idepth_slab[src];
+            // (no gradient slab: the Tracker's gradient recipe evaluated here, same function as k_gradients)
+            const uint32_t pair = grad_slab ? grad_slab[src] : grad_pair_at(g, pyr_slab + base, scharr, l, x, y);
+            const uint8_t t8 = pyr_slab[src];
+            if (!isnan(d)) {
+                rho = d;
+                gr = rec_pack_grad(pair);
+                tm = __half_as_ushort(__float2half_rn(float(t8)));  // 0..255: exact in f16
+            }
         }
+        s[tile_rho_word(j, lane)] = __float_as_uint(rho);
+        s[tile_grad_word(j, lane)] = gr;
+        reinterpret_cast<unsigned short*>(s)[tile_tmpl_half(j, lane)] = tm;
     }
-    s_tile[tile_rho_word(j, lane)] = __float_as_uint(rho);
-    s_tile[tile_grad_word(j, lane)] = gr;
-    reinterpret_cast<unsigned short*>(s_tile)[tile_tmpl_half(j, lane)] = tm;
-    __syncthreads();
+    __syncwarp();
     uint4* st = reinterpret_cast<uint4*>(pts_slab + (size_t(it) * g.tile_total + tile) * kTileWords);
-    if (threadIdx.x < kTileWords / 4) st[threadIdx.x] = reinterpret_cast<const uint4*>(s_tile)[threadIdx.x];
+    for (int i = lane; i < kTileWords / 4; i += 32) st[i] = reinterpret_cast<const uint4*>(s)[i];
 }
-static_assert(kTileWords % 4 == 0 && kTileWords / 4 <= kTileSlots, "one 16-byte store per thread moves a tile");
+static_assert(kTileWords % 4 == 0, "16-byte stores move a tile");
 
 // Row K for tiled records: partial sums of J J^T over the valid slots of a chunk of kHChunkTiles tiles and their count.
 static_assert(kTileHalfCols % 2 == 0 && (kTileRows * kTileHalfCols) % 2 == 0 && kTileSlots % 2 == 0, "8-byte loads of a lane's half row");
@@ -643,7 +652,7 @@ __global__ void __launch_bounds__(512) k_h_total_tiled(const Geom g, const Level
                 if (isnan(rho) || rho == 0.0f) continue;
                 ++valid;
                 float J[6];
-                jacobian_at<true>(rec_gx(gr), rec_gy(gr), float(kTileCols * tx + kTileHalfCols * h + c), y, rho, k, J);
+                jacobian_exact(rec_gx(gr), rec_gy(gr), float(kTileCols * tx + kTileHalfCols * h + c), y, rho, k, J);
                 h_accumulate(J, acc);
             }
         }
@@ -812,8 +821,8 @@ void launch_h_total(Launcher& L, const Geom& g, const Intrinsics* intr, const ui
 void launch_tile_records(Launcher& L, const Geom& g, const Intrinsics* intr, int scharr, const float* idepth_slab, const uint8_t* pyr_slab,
                          const uint32_t* grad_slab, int* n_points, uint32_t* pts_slab, double* h_part, double* h_total, const int* items,
                          int m) {
-    dim3 grid(g.tile_total, m);
-    k_tile_records<<<grid, kTileSlots, 0, L.stream>>>(g, scharr, idepth_slab, pyr_slab, grad_slab, pts_slab, items);
+    dim3 grid((g.tile_total + kTileCtaWarps - 1) / kTileCtaWarps, m);
+    k_tile_records<<<grid, kTileCtaWarps * 32, 0, L.stream>>>(g, scharr, idepth_slab, pyr_slab, grad_slab, pts_slab, items);
     const HChunks hc = h_chunks(g, true);
     dim3 gridh(hc.off[kMaxLevels], m), gridf(g.L, m);
     k_h_total_tiled<<<gridh, 512, 0, L.stream>>>(g, level_intrinsics(g, intr), hc, pts_slab, h_part, items);

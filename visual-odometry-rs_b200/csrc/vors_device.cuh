@@ -213,6 +213,25 @@ __device__ __forceinline__ void jacobian_centred(float gu, float gv, float a, fl
     }
 }
 
+// The reference's own expression (inverse_compositional.rs:326-340) with every operation rounded separately (no FMA
+// contraction, true divisions): the reference's J bit for bit, whatever code surrounds the call.  For the places that
+// evaluate J once per keyframe (H_total): there the contraction the compiler picks for jacobian_at would otherwise change
+// with the loop structure of the kernel, and with it the last bit of J.
+__device__ __forceinline__ void jacobian_exact(float gu, float gv, float u, float v, float z, const Intrinsics& k, float J[6]) {
+    const float a = __fsub_rn(u, k.cx), b = __fsub_rn(v, k.cy);
+    const float c = __fsub_rn(__fmul_rn(a, k.fy), __fmul_rn(k.s, b));
+    const float _fv = __fdiv_rn(1.0f, k.fy);
+    const float _fuv = __fdiv_rn(1.0f, __fmul_rn(k.fx, k.fy));
+    J[0] = __fmul_rn(__fmul_rn(gu, z), k.fx);
+    J[1] = __fmul_rn(z, __fadd_rn(__fmul_rn(gu, k.s), __fmul_rn(gv, k.fy)));
+    J[2] = __fmul_rn(-z, __fadd_rn(__fmul_rn(gu, a), __fmul_rn(gv, b)));
+    J[3] = __fadd_rn(__fmul_rn(gu, __fsub_rn(__fmul_rn(__fmul_rn(-a, b), _fv), k.s)),
+                     __fmul_rn(gv, __fsub_rn(__fmul_rn(__fmul_rn(-b, b), _fv), k.fy)));
+    J[4] = __fadd_rn(__fmul_rn(gu, __fadd_rn(__fmul_rn(__fmul_rn(a, c), _fuv), k.fx)), __fmul_rn(gv, __fmul_rn(__fmul_rn(b, c), _fuv)));
+    J[5] = __fadd_rn(__fmul_rn(__fmul_rn(gu, __fadd_rn(__fmul_rn(__fmul_rn(-k.fx, k.fx), b), __fmul_rn(k.s, c))), _fuv),
+                     __fmul_rn(gv, __fdiv_rn(c, k.fx)));
+}
+
 // ---- launchers implemented in image_kernels.cu -------------------------------------------------
 // `items`: device array of stream indices the kernels operate on (m of them); nullptr = 0..m-1.
 struct Launcher {
