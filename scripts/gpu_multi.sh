@@ -1,9 +1,9 @@
 #!/bin/bash
-# multi-GPU bench lines (run under `gpurun --gpus N`): default workload, config 4 (one alignment per GPU + gather), config 5 (1080p streams)
+# multi-GPU bench lines (run under `gpurun --gpus N`; every launch under its own `timeout`: a hung collective must not hold the box): default workload, config 4 (one alignment per GPU + gather), config 5 (1080p streams)
 N=${1:-8}
 mkdir -p gpurun_out
 run() {  # name, extra args
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 20 --warmup 5 $2 \
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 20 --warmup 5 $2 \
       > gpurun_out/r02_bench_$1_${N}gpu.json 2> gpurun_out/r02_bench_$1_${N}gpu.err; echo "$1 N=$N rc=$?"
   python -c "
 import json,sys; d=json.load(open('gpurun_out/r02_bench_$1_${N}gpu.json')); r=d['roofline']
