@@ -63,6 +63,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gather-every", type=int, default=4, help="multi-GPU: steps of pose records per all-gather (SURVEY §5)")
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs index + 1 (default 2 = configs[1])")
     ap.add_argument("--streams", type=int, default=0, help="independent RGB-D streams per GPU (0 = the config's default; 296 = 2 CTAs x 148 SMs)")
     ap.add_argument("--team", type=int, default=0, help="CTAs per alignment (0 = auto)")
@@ -92,17 +93,57 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).  NVML is polled from a thread
+    every 5 ms (a 20-step timed region is ~0.1 s: `nvidia-smi -lms` often has not printed its first line by then); without
+    pynvml it falls back to an `nvidia-smi -lms 50` child process."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASON_BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.rows = []
+        self.samples = []  # NVML: (sm MHz, max sm MHz, reason bit mask)
         self.proc = None
+        self.nv = None
+        self._stop = threading.Event()
+
+    def _nvml_handle(self, nv):
+        try:  # CUDA_VISIBLE_DEVICES may renumber the devices: go by UUID
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            return nv.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        except Exception:
+            return nv.nvmlDeviceGetHandleByIndex(self.gpu)
+
+    def _poll(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((float(sm), float(mx), int(mask)))
+            except Exception:
+                return
+            self._stop.wait(0.005)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.h = self._nvml_handle(nv)
+            nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)  # fails here, not in the thread, if NVML cannot serve us
+            self.nv = nv
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -116,6 +157,13 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nv is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            sm = [x[0] for x in self.samples]
+            reasons = sorted({name for _, _, mask in self.samples for name, bit in self.REASON_BITS if mask & bit})
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(x[1] for x in self.samples) if sm else None,
+                    "samples": len(sm), "reasons": reasons, "source": "nvml, 5 ms period"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -136,7 +184,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 50"}
 
 
 def make_streams(cfg, n_streams, n_frames, seed0, device, **traj_kw):
@@ -222,53 +270,32 @@ def run_ours(args):
     stats_i32 = np.frombuffer(stats, dtype=np.int32).reshape(B, -1)  # column 1 = keyframe_changed (vors_track_stats)
     P = 0 if args.no_parity else min(args.parity_streams, B)
 
-    # Streams shard across ranks with no data-path collective; the only exchange is one all-gather of 32-byte pose records
-    # per step.  It is asynchronous: submitted after step k, it completes while step k + 1 runs; collected one step late.
-    pg = shard.PoseGatherer(B * world, device=device, depth=2) if world > 1 else None
-    gathered = [0]
-    # The exchange's host work (packing, enqueueing the copies and the collective, collecting the previous one) runs on a helper
-    # thread while the main thread is inside the next track call (ctypes releases the GIL): off the critical path on the host too.
-    import concurrent.futures as cf
-    xpool = cf.ThreadPoolExecutor(max_workers=1) if pg is not None else None
-    pending_x = [None]
-    def exchange_work(p, st):
-        torch.cuda.set_device(local)
-        if pg.in_flight() == pg.depth:
-            pg.collect()
-            gathered[0] += 1
-        pg.submit(p, st)
+    # Streams shard across ranks with no data-path collective; the only exchange is an all-gather of 32-byte pose records,
+    # `--gather-every` steps at a time.  It is asynchronous: handed to a helper thread after a step, it completes
+    # while the next steps run (the helper's host work overlaps the main thread's track call: ctypes releases the GIL).
+    xch = (shard.StepExchange(B, device=device, group=args.gather_every, depth=2, thread_init=lambda: torch.cuda.set_device(local))
+           if world > 1 else None)
     def exchange(bt):
-        if pg is None:
-            return
-        if pending_x[0] is not None:
-            pending_x[0].result()
-        _, p = bt.current_frames()
-        pending_x[0] = xpool.submit(exchange_work, p, status.copy())
+        if xch is not None:
+            xch.push(bt.current_frames()[1], status)
     def drain():
-        if pg is None:
-            return
-        if pending_x[0] is not None:
-            pending_x[0].result()
-            pending_x[0] = None
-        while pg.in_flight():
-            last = pg.collect()
-            gathered[0] += 1
-            assert last.shape == (B * world, shard.POSE_RECORD_FLOATS)
+        if xch is not None:
+            xch.drain()
 
     def new_tracker():
         return vb.BatchTracker(vcfg, ts[0], depth_h[0].numpy(), ts[0], gray_h[0].numpy(), layout=vb.ROW_MAJOR)
 
     def barrier():
         # (collectives are enqueued in the same order on every rank: the helper thread's exchange first)
-        if pending_x[0] is not None:
-            pending_x[0].result()
+        if xch is not None:
+            xch.wait_enqueued()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if pending_x[0] is not None:
-            pending_x[0].result()
+        if xch is not None:
+            xch.wait_enqueued()
         if world > 1:
             t = torch.tensor([x], dtype=torch.float64, device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -375,7 +402,7 @@ def run_ours(args):
                        "team_size": args.team or "auto", "ctas_per_alignment": launch_shape[0], "alignments_in_flight": launch_shape[1],
                        "keyframe_switches_per_step": switches / K,
                        "failed_alignments": failed,
-                       "pose_gather": (f"async NCCL all_gather_into_tensor per step on a side stream and a helper host thread, {gathered[0]} exchanges collected one step late"
+                       "pose_gather": (f"async NCCL all_gather_into_tensor of {args.gather_every} steps' pose records at a time on a side stream, driven by a helper host thread; {xch.blocks} blocks collected"
                                        if world > 1 else "none (1 GPU)"),
                        "max_pose_error_vs_ground_truth": {"rad": rot_err, "m": trans_err},
                        "arms_max_abs_pose_diff": float(np.max(np.abs(poses_a - poses_b))), "synth_seconds": gen_s,

@@ -70,6 +70,27 @@ def _worker(rank, world, port, q):
     while pg2.in_flight():
         got.append(pg2.collect())
     assert len(got) == 5 and all(np.array_equal(g[:, :7], full[:, :7] + float(k)) for k, g in enumerate(got))
+    # the grouped form bench.py steps with: 3 steps per block, 7 steps (so the last block is partial), a main-thread
+    # collective in the middle, 4 streams per rank; record (step k, global stream s) carries k + s / 100
+    n_loc, G = 4, 3
+    xch = shard.StepExchange(n_loc, device="cpu", group=G, keep=True)
+    mine = rank + world * np.arange(n_loc)
+    for k in range(7):
+        p = np.repeat((k + mine / 100.0).astype(np.float32)[:, None], 7, 1)
+        xch.push(p, (mine % 2).astype(np.float32))
+        if k == 3:
+            xch.wait_enqueued()
+            dist.barrier()
+    xch.drain()
+    assert xch.blocks == 3 and len(xch.collected) == 3
+    every = np.arange(n_loc * world)
+    for blk_i, blk in enumerate(xch.collected):
+        assert blk.shape == (G, n_loc * world, 8)
+        for gstep in range(G):
+            k = blk_i * G + gstep
+            want = (k + every / 100.0).astype(np.float32) if k < 7 else np.zeros(n_loc * world, np.float32)
+            assert np.array_equal(blk[gstep, :, 0], want) and np.array_equal(blk[gstep, :, 6], want), (blk_i, gstep)
+            assert np.array_equal(blk[gstep, :, 7], (every % 2).astype(np.float32) if k < 7 else np.zeros(n_loc * world, np.float32))
     q.put((rank, full))
     dist.barrier()
     dist.destroy_process_group()

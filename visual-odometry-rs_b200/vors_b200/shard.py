@@ -139,3 +139,78 @@ class PoseGatherer:
 
     def in_flight(self) -> int:
         return len(self._pending)
+
+
+class StepExchange:
+    """The stepping loop's side of the pose exchange: local records of `group` consecutive steps are accumulated on the host
+    and exchanged as ONE block ("or every K steps"), through a `PoseGatherer` driven from a helper thread, so
+    that neither the collective nor its host work sits between two launches of the align kernel.
+
+      push(poses, status)   after every step (main thread); every `group`-th call hands the block to the helper thread
+      wait_enqueued()       the main thread calls this before any collective of its own: all ranks must enqueue their
+                            collectives in the same order, and the helper's exchange comes first
+      drain()               flushes a partial block and collects everything in flight
+
+    Every rank owns `n_local` streams (weak scaling); stream j of rank r is global stream r + j * world, as in `partition`.
+    A collected block is [group, n_local * world, 8] in global stream order (rows of steps not reached yet are zero)."""
+
+    def __init__(self, n_local: int, device=None, group: int = 4, depth: int = 2, thread_init=None, keep: bool = False):
+        import concurrent.futures as cf
+        import torch.distributed as dist
+
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.n_local, self.group, self.world = int(n_local), max(1, int(group)), world
+        self.n_step = self.n_local * world
+        # items = (step of the group, global stream): item % world is the owner, so `partition` hands every rank its own
+        # streams of every step, step-major - the order of the accumulation buffer below
+        self.pg = PoseGatherer(self.n_step * self.group, device=device, depth=depth)
+        assert self.pg.n_local == self.n_local * self.group
+        self._p = np.zeros((self.group, self.n_local, 7), np.float32)
+        self._s = np.zeros((self.group, self.n_local), np.float32)
+        self._fill = 0
+        self._pool = cf.ThreadPoolExecutor(max_workers=1)
+        self._pending = None
+        self._thread_init = thread_init
+        self.keep = keep
+        self.collected = []  # blocks, oldest first (only with keep=True)
+        self.blocks = 0      # blocks collected so far
+
+    def _collect_one(self):
+        full = self.pg.collect().reshape(self.group, self.n_step, POSE_RECORD_FLOATS)
+        self.blocks += 1
+        if self.keep:
+            self.collected.append(full)
+
+    def _work(self, p, s):
+        if self._thread_init is not None:
+            self._thread_init()
+        if self.pg.in_flight() == self.pg.depth:
+            self._collect_one()
+        self.pg.submit(p, s)
+
+    def push(self, poses: np.ndarray, status: np.ndarray) -> None:
+        self._p[self._fill] = poses
+        self._s[self._fill] = status
+        self._fill += 1
+        if self._fill == self.group:
+            self.flush()
+
+    def flush(self) -> None:
+        if self._fill == 0:
+            return
+        self._p[self._fill:] = 0.0
+        self._s[self._fill:] = 0.0
+        self.wait_enqueued()
+        self._pending = self._pool.submit(self._work, self._p.reshape(-1, 7).copy(), self._s.reshape(-1).copy())
+        self._fill = 0
+
+    def wait_enqueued(self) -> None:
+        if self._pending is not None:
+            self._pending.result()
+            self._pending = None
+
+    def drain(self) -> None:
+        self.flush()
+        self.wait_enqueued()
+        while self.pg.in_flight():
+            self._collect_one()
