@@ -93,57 +93,22 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).  NVML is polled from a thread
-    every 5 ms (a 20-step timed region is ~0.1 s: `nvidia-smi -lms` often has not printed its first line by then); without
-    pynvml it falls back to an `nvidia-smi -lms 50` child process."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md's clocks line), from an `nvidia-smi -lms`
+    child process: it is started before the warm-up (its first line takes longer than a 20-step timed region), every line is
+    stamped when it arrives, and `stop()` keeps the lines that fall between `begin()` and `stop()`.
+    (Polling NVML from a thread of THIS process was tried and rejected: each query holds a driver lock for milliseconds and
+    the kernel launches of the timed loop queue up behind it - 5.3 -> 6.9 ms per step.)"""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    REASON_BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.rows = []
-        self.samples = []  # NVML: (sm MHz, max sm MHz, reason bit mask)
+        self.rows = []  # (arrival time, fields)
         self.proc = None
-        self.nv = None
-        self._stop = threading.Event()
-
-    def _nvml_handle(self, nv):
-        try:  # CUDA_VISIBLE_DEVICES may renumber the devices: go by UUID
-            import torch
-            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
-            return nv.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
-        except Exception:
-            return nv.nvmlDeviceGetHandleByIndex(self.gpu)
-
-    def _poll(self):
-        nv = self.nv
-        while not self._stop.is_set():
-            try:
-                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
-                try:
-                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                self.samples.append((float(sm), float(mx), int(mask)))
-            except Exception:
-                return
-            self._stop.wait(0.005)
+        self.t_begin = None
 
     def start(self):
-        try:
-            import pynvml as nv
-            nv.nvmlInit()
-            self.h = self._nvml_handle(nv)
-            nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)  # fails here, not in the thread, if NVML cannot serve us
-            self.nv = nv
-            self.thread = threading.Thread(target=self._poll, daemon=True)
-            self.thread.start()
-            return
-        except Exception:
-            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -152,18 +117,15 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def begin(self):
+        self.t_begin = time.perf_counter()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
-        if self.nv is not None:
-            self._stop.set()
-            self.thread.join(timeout=2)
-            sm = [x[0] for x in self.samples]
-            reasons = sorted({name for _, _, mask in self.samples for name, bit in self.REASON_BITS if mask & bit})
-            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(x[1] for x in self.samples) if sm else None,
-                    "samples": len(sm), "reasons": reasons, "source": "nvml, 5 ms period"}
+        t_end = time.perf_counter()
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -171,10 +133,14 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        inside = [r for t, r in self.rows if t0 <= t <= t_end and len(r) >= 9]
+        where = "inside the timed region"
+        if not inside:  # a very short region between two lines: the line that arrived last before its end
+            before = [r for t, r in self.rows if t <= t_end and len(r) >= 9]
+            inside, where = before[-1:], "last line before the end of the timed region (none fell inside)"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            if len(r) < 9:
-                continue
+        for r in inside:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -184,7 +150,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 50"}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 50, " + where}
 
 
 def make_streams(cfg, n_streams, n_frames, seed0, device, **traj_kw):
@@ -314,6 +280,8 @@ def run_ours(args):
         # the next step's device buffer is announced: its copy into the frame pyramids and the pyramid build overlap this alignment
         return bt.track_device(ts[k].ctypes.data, depth_cm[fi(k)].data_ptr(), ts[k].ctypes.data, gray_cm[fi(k)].data_ptr(),
                                status.ctypes.data, C.addressof(stats), gray_cm[fi(k + 1)].data_ptr() if k < T else None)
+    if rank == 0:
+        sampler.start()  # (before the warm-up: nvidia-smi needs longer than a short timed region to print its first line)
     for k in range(1, W + 1):
         step_device(k)
         exchange(bt)
@@ -321,8 +289,7 @@ def run_ours(args):
     align_ms = pyr_ms = kf_ms = up_ms = 0.0
     launches = point_passes = switches = failed = 0
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.begin()
     t_start = time.perf_counter()
     for k in range(W + 1, T + 1):
         step_device(k)
