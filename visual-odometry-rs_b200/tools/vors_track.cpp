@@ -6,8 +6,7 @@
 // PNG (converted to luma like image::open().to_luma(), vors_track.rs:143), tracks every frame through the C ABI
 // (Config::init / Tracker::track / Tracker::current_frame) and prints one TUM trajectory line per frame to stdout:
 // `timestamp tx ty tz qx qy qz qw` (src/dataset/tum_rgbd.rs:76-86).  Diagnostics go to stderr like the reference's
-// eprintln! calls.  PNG decoding is a small zlib-based reader (8/16-bit gray, RGB, RGBA, gray+alpha, non-interlaced).
-#include <zlib.h>
+// eprintln! calls.  PNG decoding: tools/png_reader.h (zlib only; gray, RGB(A), palette, interlaced or not, CRC-checked).
 
 #include <charconv>
 #include <cmath>
@@ -21,126 +20,14 @@
 #include <vector>
 
 #include "../../include/vors_b200.h"
+#include "png_reader.h"
 
 namespace {
 
 const char* kUsage = "Usage: ./vors_track [fr1|fr2|fr3|icl] associations_file";
 
-struct Png {
-    uint32_t width = 0, height = 0;
-    int bit_depth = 0, channels = 0;
-    std::vector<uint8_t> data;  // height x width x channels x (bit_depth / 8), row-major, big-endian samples
-};
-
-uint32_t be32(const uint8_t* p) { return (uint32_t(p[0]) << 24) | (uint32_t(p[1]) << 16) | (uint32_t(p[2]) << 8) | p[3]; }
-
-bool read_file(const std::string& path, std::vector<uint8_t>& out) {
-    std::ifstream f(path, std::ios::binary);
-    if (!f) return false;
-    out.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
-    return true;
-}
-
-bool decode_png(const std::string& path, Png& png, std::string& err) {
-    std::vector<uint8_t> file;
-    if (!read_file(path, file)) { err = "cannot open " + path; return false; }
-    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
-    if (file.size() < 8 || std::memcmp(file.data(), sig, 8) != 0) { err = path + ": not a PNG file"; return false; }
-    std::vector<uint8_t> idat;
-    int color_type = -1, interlace = 0;
-    size_t pos = 8;
-    while (pos + 12 <= file.size()) {
-        const uint32_t len = be32(&file[pos]);
-        const char* type = reinterpret_cast<const char*>(&file[pos + 4]);
-        if (pos + 12 + len > file.size()) break;
-        const uint8_t* body = &file[pos + 8];
-        if (!std::memcmp(type, "IHDR", 4) && len >= 13) {
-            png.width = be32(body);
-            png.height = be32(body + 4);
-            png.bit_depth = body[8];
-            color_type = body[9];
-            interlace = body[12];
-        } else if (!std::memcmp(type, "IDAT", 4)) {
-            idat.insert(idat.end(), body, body + len);
-        } else if (!std::memcmp(type, "IEND", 4)) {
-            break;
-        }
-        pos += 12 + len;
-    }
-    switch (color_type) {
-        case 0: png.channels = 1; break;
-        case 2: png.channels = 3; break;
-        case 4: png.channels = 2; break;
-        case 6: png.channels = 4; break;
-        default: err = path + ": unsupported PNG colour type (palette images are not supported)"; return false;
-    }
-    if (interlace != 0 || (png.bit_depth != 8 && png.bit_depth != 16)) { err = path + ": unsupported PNG (interlaced or bit depth != 8/16)"; return false; }
-    const size_t bpp = size_t(png.channels) * size_t(png.bit_depth / 8);
-    const size_t stride = size_t(png.width) * bpp;
-    std::vector<uint8_t> raw((stride + 1) * png.height);
-    uLongf raw_len = uLongf(raw.size());
-    if (uncompress(raw.data(), &raw_len, idat.data(), uLong(idat.size())) != Z_OK || raw_len != raw.size()) {
-        err = path + ": corrupt PNG data";
-        return false;
-    }
-    png.data.assign(stride * png.height, 0);
-    std::vector<uint8_t> zero(stride, 0);
-    for (uint32_t y = 0; y < png.height; ++y) {
-        const uint8_t filter = raw[(stride + 1) * y];
-        const uint8_t* in = &raw[(stride + 1) * y + 1];
-        uint8_t* out = &png.data[stride * y];
-        const uint8_t* up = y ? &png.data[stride * (y - 1)] : zero.data();
-        for (size_t i = 0; i < stride; ++i) {
-            const int a = i >= bpp ? out[i - bpp] : 0, b = up[i], c = i >= bpp ? up[i - bpp] : 0;
-            int pred = 0;
-            switch (filter) {
-                case 0: pred = 0; break;
-                case 1: pred = a; break;
-                case 2: pred = b; break;
-                case 3: pred = (a + b) / 2; break;
-                case 4: {
-                    const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
-                    pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
-                    break;
-                }
-                default: err = path + ": bad PNG filter"; return false;
-            }
-            out[i] = uint8_t(in[i] + pred);
-        }
-    }
-    return true;
-}
-
-// helper::read_png_16bits (src/misc/helper.rs:13-36): 16-bit gray PNG, samples are big-endian.
-bool read_depth(const std::string& path, uint32_t& w, uint32_t& h, std::vector<uint16_t>& out, std::string& err) {
-    Png png;
-    if (!decode_png(path, png, err)) return false;
-    if (png.bit_depth != 16 || png.channels != 1) { err = path + ": depth image must be a 16-bit gray PNG"; return false; }
-    w = png.width; h = png.height;
-    out.resize(size_t(w) * h);
-    for (size_t i = 0; i < out.size(); ++i) out[i] = uint16_t((png.data[2 * i] << 8) | png.data[2 * i + 1]);
-    return true;
-}
-
-// image::open(path).to_luma() (vors_track.rs:143).  image 0.19 converts RGB to luma in f32 with the BT.709 weights and a
-// truncating cast (recalled behaviour of the un-vendored crate); gray images pass through; 16-bit samples keep the high byte.
-bool read_gray(const std::string& path, uint32_t& w, uint32_t& h, std::vector<uint8_t>& out, std::string& err) {
-    Png png;
-    if (!decode_png(path, png, err)) return false;
-    w = png.width; h = png.height;
-    out.resize(size_t(w) * h);
-    const int bytes = png.bit_depth / 8, ch = png.channels;
-    for (size_t i = 0; i < out.size(); ++i) {
-        const uint8_t* p = &png.data[i * size_t(ch) * size_t(bytes)];
-        if (ch <= 2) {
-            out[i] = p[0];
-        } else {
-            const float l = 0.2126f * float(p[0]) + 0.7152f * float(p[bytes]) + 0.0722f * float(p[2 * bytes]);
-            out[i] = uint8_t(l);
-        }
-    }
-    return true;
-}
+using vors_png::read_depth;
+using vors_png::read_gray;
 
 struct Association {  // src/dataset/tum_rgbd.rs:64-74
     double depth_ts = 0, color_ts = 0;
