@@ -131,3 +131,18 @@ def test_pose_gatherer_single_process_is_identity():
     assert np.array_equal(out[:, :7], poses) and np.array_equal(out[:, 7], status.astype(np.float32))
     with pytest.raises(RuntimeError):
         pg.collect()
+
+
+def test_step_exchange_single_process_blocks():
+    """Without a process group the grouped exchange is the identity: blocks of `group` steps, the last one zero-padded."""
+    xch = shard.StepExchange(3, device="cpu", group=2, keep=True)
+    for k in range(5):
+        xch.push(np.full((3, 7), float(k + 1), np.float32), np.array([0, 1, 0], np.float32))
+        xch.wait_enqueued()  # (what a caller does before a collective of its own)
+    xch.drain()
+    assert xch.blocks == 3 and [b.shape for b in xch.collected] == [(2, 3, 8)] * 3
+    steps = np.concatenate([b[:, 0, 0] for b in xch.collected])
+    assert np.array_equal(steps, [1, 2, 3, 4, 5, 0])
+    assert np.array_equal(xch.collected[0][1, :, 7], [0, 1, 0]) and np.all(xch.collected[2][1] == 0)
+    xch.drain()  # idempotent
+    assert xch.blocks == 3
