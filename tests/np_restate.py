@@ -382,3 +382,185 @@ def tracker_track(state, levels_obs, coarsest, fixed_iters=0):
     with np.errstate(invalid="ignore", divide="ignore"):
         optical_flow = flow_sum / F(len(x))
     return went_well, F(optical_flow)
+
+
+# ---- inverse-depth pyramid (rows F, G) and extract_z (row H), f32, the reference's operation order --------------------------
+def idepth_level0(depth_u16, mask, scale, variance):
+    """helper::zip_mask_map + inverse_depth::from_depth (helper.rs:40-47, inverse_depth.rs:24-29): scale / depth where the
+    mask is set and depth != 0; Unknown -> (NaN, 0)."""
+    known = mask.astype(bool) & (depth_u16 != 0)
+    with np.errstate(divide="ignore"):
+        d = np.where(known, np.float32(scale) / depth_u16.astype(np.float32), np.float32(np.nan)).astype(np.float32)
+    return d, np.where(known, np.float32(variance), np.float32(0)).astype(np.float32)
+
+
+def idepth_halve_dso_mean(d, v):
+    """multires::halve (multires.rs:67-88) with inverse_depth::fuse + strategy_dso_mean (inverse_depth.rs:49-98): the known
+    children of a 2x2 bloc in (a, b, c, d) = ((2i,2j), (2i+1,2j), (2i,2j+1), (2i+1,2j+1)) order; one child is copied, more are
+    averaged with weights, sums and products rounded one by one, left to right, in f32."""
+    f = np.float32
+    hr, hc = d.shape[0] // 2, d.shape[1] // 2
+    kids = [(d[0:2 * hr:2, 0:2 * hc:2], v[0:2 * hr:2, 0:2 * hc:2]), (d[1:2 * hr:2, 0:2 * hc:2], v[1:2 * hr:2, 0:2 * hc:2]),
+            (d[0:2 * hr:2, 1:2 * hc:2], v[0:2 * hr:2, 1:2 * hc:2]), (d[1:2 * hr:2, 1:2 * hc:2], v[1:2 * hr:2, 1:2 * hc:2])]
+    count = np.zeros((hr, hc), np.int32)
+    first_d = np.full((hr, hc), np.nan, f)
+    first_v = np.zeros((hr, hc), f)
+    num = np.zeros((hr, hc), f)
+    den = np.zeros((hr, hc), f)
+    for kd, kv in kids:
+        known = ~np.isnan(kd)
+        prod = (np.where(known, kd, f(0)) * kv).astype(f)           # d_k * v_k, rounded
+        is_first = known & (count == 0)
+        first_d = np.where(is_first, kd, first_d)
+        first_v = np.where(is_first, kv, first_v)
+        num = np.where(is_first, prod, np.where(known, (num + prod).astype(f), num))   # ((d1 v1 + d2 v2) + d3 v3) + d4 v4
+        den = np.where(is_first, kv, np.where(known, (den + kv).astype(f), den))        # ((v1 + v2) + v3) + v4
+        count += known
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mean = (num / den).astype(f)
+    out_d = np.where(count == 0, f(np.nan), np.where(count == 1, first_d, mean)).astype(f)
+    out_v = np.where(count == 0, f(0), np.where(count == 1, first_v, den)).astype(f)
+    return out_d, out_v
+
+
+def idepth_pyramid(depth_u16, mask, scale, variance, nb_levels):
+    """multires::limited_sequence(nb_levels, level 0, halve) (inverse_compositional.rs:127-138)."""
+    levels = [idepth_level0(depth_u16, mask, scale, variance)]
+    while len(levels) < nb_levels and min(levels[-1][0].shape) >= 2:
+        levels.append(idepth_halve_dso_mean(*levels[-1]))
+    return levels
+
+
+def extract_z(d):
+    """extract_z (inverse_compositional.rs:260-279): known inverse depths in the matrix' (column-major) iteration order with
+    their (u = column, v = row) coordinates."""
+    cols, rows = np.nonzero(~np.isnan(d.T))
+    return np.stack([cols, rows], 1), d[rows, cols]
+
+
+# ---- candidates::dso::select (row R), restated from candidates/dso.rs:98-325 with the DEFAULT_* configurations (:72-90) ------
+def _splitmix64(state):
+    """The seeded generator that stands in for `rand::thread_rng()` (dso.rs:142) in the oracle and in the CUDA path."""
+    M = (1 << 64) - 1
+    state = (state + 0x9E3779B97F4A7C15) & M
+    z = state
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+    return state, z ^ (z >> 31)
+
+
+def _ceil_div(n, d):
+    q, r = divmod(n, d)
+    return q if r == 0 else q + 1
+
+
+def dso_region_medians(g, size=32):
+    """region_median_gradients (dso.rs:307-325): sorted region values, element len / 2."""
+    rows, cols = g.shape
+    out = np.zeros((_ceil_div(rows, size), _ceil_div(cols, size)), np.uint16)
+    for i in range(out.shape[0]):
+        for j in range(out.shape[1]):
+            v = np.sort(g[i * size:min(rows, (i + 1) * size), j * size:min(cols, (j + 1) * size)].reshape(-1))
+            out[i, j] = v[len(v) // 2]
+    return out
+
+
+def dso_region_thresholds(med, a=1.0, b=3):
+    """region_thresholds (dso.rs:275-303): 3x3 (clipped) sum IN u16 ARITHMETIC (release builds wrap), mean + b in f32, squared,
+    cast back to u16 (truncating; None -> the reference panics: returned as None here)."""
+    f = np.float32
+    rows, cols = med.shape
+    out = np.zeros((rows, cols), np.uint16)
+    for i in range(rows):
+        for j in range(cols):
+            blk = med[max(0, i - 1):min(rows, i + 2), max(0, j - 1):min(cols, j + 2)]
+            s = int(blk.astype(np.int64).sum()) & 0xFFFF
+            t = f(f(s) / f(blk.size)) + f(b)
+            sq = f(f(f(a) * t) * t)
+            if not (sq < f(65536.0)):
+                return None
+            out[i, j] = int(sq)
+    return out
+
+
+def dso_pick_all(g, thresholds, base_size, nb_levels=3, threshold_factor=0.5, region_size=32):
+    """pick_all_block_candidates (dso.rs:154-187) with init_max_gradients (:190-216), max_of_four_gradients (:219-233) and
+    pick_level_block_candidates (:240-270).  Returns (number picked, picked levels u8 [rows, cols])."""
+    f = np.float32
+    rows, cols = g.shape
+    br, bc = _ceil_div(rows, base_size), _ceil_div(cols, base_size)
+    # init_max_gradients: first strict maximum scanning the block column by column
+    mg = np.zeros((br, bc), np.int64)   # value
+    mi = np.zeros((br, bc), np.int64)
+    mj = np.zeros((br, bc), np.int64)
+    for bi in range(br):
+        for bj in range(bc):
+            blk = g[bi * base_size:min(rows, (bi + 1) * base_size), bj * base_size:min(cols, (bj + 1) * base_size)]
+            k = int(np.argmax(blk.T.reshape(-1)))  # column-major scan; argmax returns the FIRST maximum = strict `>` update
+            mg[bi, bj] = blk.T.reshape(-1)[k]
+            mj[bi, bj] = bj * base_size + k // blk.shape[0]
+            mi[bi, bj] = bi * base_size + k % blk.shape[0]
+    levels = [(mg, mi, mj)]
+    while len(levels) < nb_levels and min(levels[-1][0].shape) >= 2:  # multires::limited_sequence + halve
+        pg, pi, pj = levels[-1]
+        hr, hc = pg.shape[0] // 2, pg.shape[1] // 2
+        ng, ni, nj = np.zeros((hr, hc), np.int64), np.zeros((hr, hc), np.int64), np.zeros((hr, hc), np.int64)
+        for i in range(hr):
+            for j in range(hc):
+                best = None
+                # g_max(g1, g_max(g2, g_max(g3, g4))), `if m1 < m2 { m2 } else { m1 }`: fold from the right, ties keep the left
+                for (a, b_) in ((2 * i + 1, 2 * j + 1), (2 * i, 2 * j + 1), (2 * i + 1, 2 * j), (2 * i, 2 * j)):
+                    cand = (pg[a, b_], pi[a, b_], pj[a, b_])
+                    best = cand if best is None or not (cand[0] < best[0]) else best
+                ng[i, j], ni[i, j], nj[i, j] = best
+        levels.append((ng, ni, nj))
+    picked = np.zeros((rows, cols), np.uint8)
+    mask = np.ones((br, bc), bool)
+    coef = f(1.0)
+    total = 0
+    for level, (lg, li, lj) in enumerate(levels):
+        mh, mw = mask.shape
+        nxt = np.ones((mh // 2, mw // 2), bool)
+        for j in range(mw // 2 * 2):
+            for i in range(mh // 2 * 2):
+                if mask[i, j]:
+                    th = thresholds[li[i, j] // region_size, lj[i, j] // region_size]
+                    if f(lg[i, j]) >= f(coef * f(th)):
+                        nxt[i // 2, j // 2] = False
+                        picked[li[i, j], lj[i, j]] = level + 1
+                        total += 1
+                else:
+                    nxt[i // 2, j // 2] = False
+        mask = nxt
+        coef = f(coef * f(threshold_factor))
+    return total, picked
+
+
+def dso_select(g, nb_target, nb_iterations_left, seed, base_size=4):
+    """select (dso.rs:98-147).  Returns (mask, number of block candidates of the last iteration, used the random branch) or
+    None where the reference would panic (threshold out of u16)."""
+    f = np.float32
+    th = dso_region_thresholds(dso_region_medians(g))
+    if th is None:
+        return None
+    while True:
+        nb, picked = dso_pick_all(g, th, base_size)
+        ratio = f(f(nb) / f(nb_target))
+        target_f = f(f(np.sqrt(ratio)) * f(f(base_size) + f(1.0)) - f(1.0))
+        rounded = int(np.floor(abs(float(target_f)) + 0.5)) * (1 if target_f >= 0 else -1)  # f32::round: half away from zero
+        target_size = max(1, rounded)
+        if ratio < f(0.8) or ratio > f(4.0):
+            if target_size != base_size and nb_iterations_left > 0:
+                base_size, nb_iterations_left = target_size, nb_iterations_left - 1
+                continue
+            return picked > 0, nb, False
+        if ratio > f(1.1):
+            lim = int(f(255.0) / ratio) & 0xFF
+            mask = np.zeros(picked.shape, bool)
+            state = seed
+            cols_, rows_ = np.nonzero(picked.T > 0)  # `picked.map` walks column-major; one draw per picked pixel
+            for c, r in zip(cols_, rows_):
+                state, z = _splitmix64(state)
+                mask[r, c] = (z & 0xFF) <= lim
+            return mask, nb, True
+        return picked > 0, nb, False

@@ -133,6 +133,39 @@ def test_idepth_pyramid_and_extract_order(oracle, small_pair):
         assert np.array_equal(idepth, dl[rows, cols])
 
 
+def test_idepth_pyramid_bit_for_bit_against_numpy_restatement(oracle, small_pair):
+    """Rows F, G, H: the oracle's inverse-depth pyramid (from_depth, halve + fuse + strategy_dso_mean) and extract_z against
+    the independent f32 numpy restatement in np_restate.py - every value and weight bit for bit, on a depth map with holes whose
+    odd borders produce 1-, 2-, 3- and 4-child blocs, for the Tracker's coarse-to-fine mask and for the dense extension."""
+    import np_restate as R
+
+    scene, f0, _, _ = small_pair
+    depth = f0[1].copy()
+    depth[10:31, 20:51] = 0
+    depth[40, 100] = depth[40, 101] = depth[41, 100] = 0
+    depth[77:, 3] = 0
+    for mode in (0, 1):
+        cfg = _cfg(oracle, scene, nb_levels=5, candidate_mode=mode)
+        kf = oracle.Keyframe(cfg, depth, f0[0])
+        mask = kf.mask0() if mode == 0 else np.ones(depth.shape, bool)
+        levels = R.idepth_pyramid(depth, mask, cfg.depth_scale, cfg.idepth_variance, 5)
+        assert len(levels) == kf.levels == 5
+        child_counts = set()
+        for l, (d, v) in enumerate(levels):
+            od, ov = kf.idepth_map(l)
+            assert np.array_equal(np.isnan(od), np.isnan(d)), (mode, l)
+            assert np.array_equal(od.view(np.uint32)[~np.isnan(d)], d.view(np.uint32)[~np.isnan(d)]), (mode, l)
+            assert np.array_equal(ov.view(np.uint32), v.view(np.uint32)), (mode, l)
+            xy, z = R.extract_z(d)
+            oxy, oz, _ = kf.points(l, with_jac=False)
+            assert np.array_equal(oxy, xy) and np.array_equal(oz.view(np.uint32), z.view(np.uint32)), (mode, l)
+            if l:
+                pd = levels[l - 1][0]
+                hr, hc = d.shape
+                child_counts |= set(np.unique(sum((~np.isnan(pd[a:2 * hr:2, b:2 * hc:2])).astype(int) for a in (0, 1) for b in (0, 1))))
+        assert child_counts >= {0, 1, 2, 3, 4} if mode == 1 else child_counts >= {0, 1, 2}, child_counts
+
+
 def _similar_numpy(ds, vs):
     """inverse_depth.rs:105-152 restated independently (f32, the reference's operation order); returns (d, v) or None."""
     f = np.float32
@@ -335,6 +368,46 @@ def test_short_pyramid_is_rejected(oracle):
     cfg = _cfg(oracle, scene, nb_levels=6)
     with pytest.raises(ValueError):
         oracle.Tracker(cfg, 0.0, np.ones((16, 16), np.uint16), 0.0, np.zeros((16, 16), np.uint8))
+
+
+def test_dso_select_bit_for_bit_against_numpy_restatement(oracle):
+    """Row R: the oracle's `candidates::dso::select` against the independent numpy restatement written from
+    candidates/dso.rs:98-325 (np_restate.dso_select): masks, candidate counts and the branch taken are identical over random
+    heavy-tailed gradient images of awkward sizes (regions and blocks cut by the border, images smaller than a region), targets
+    that exercise every branch - accepted as is, block-size recursion (both directions, 0 / 1 / 2 iterations left), seeded
+    thinning - and the case where the reference panics (threshold beyond u16)."""
+    import np_restate as R
+
+    def oracle_dso(g, target, iters, seed):
+        rows, cols = g.shape
+        mask = np.zeros(g.size, np.uint8)
+        used = C.c_int()
+        n = oracle.lib().ref_dso_select(np.ascontiguousarray(g.T).reshape(-1), rows, cols, target, iters, seed, mask, C.byref(used))
+        return mask.reshape(cols, rows).T.astype(bool), n, bool(used.value)
+
+    rng = np.random.default_rng(5)
+    cover = {"plain": 0, "random": 0, "exhausted": 0, "recursed": 0}
+    for trial in range(21):
+        rows, cols = [(60, 80), (37, 53), (96, 64), (33, 31), (120, 160), (8, 9), (65, 130)][trial % 7]
+        g = np.minimum(rng.lognormal(np.log(4.0), [0.8, 1.2, 1.6][trial % 3], (rows, cols)), 60000).astype(np.uint16)
+        if trial % 5 == 0:
+            g[: rows // 2] //= 4  # regions with very different medians
+        for target in (20, 150, 600, 3000):
+            base = None
+            for iters in (0, 1, 2):
+                want_mask, want_n, want_random = R.dso_select(g, target, iters, 99 + trial)
+                got_mask, got_n, got_random = oracle_dso(g, target, iters, 99 + trial)
+                assert got_n == want_n and got_random == want_random and np.array_equal(got_mask, want_mask), (trial, target, iters)
+                ratio = want_n / target
+                cover["random" if want_random else "plain" if 0.8 <= ratio <= 4.0 else "exhausted"] += 1
+                if iters == 0:
+                    base = want_n
+                elif want_n != base:
+                    cover["recursed"] += 1  # another block size was tried
+    assert all(v > 0 for v in cover.values()), cover
+    # the reference's `num_traits::cast(..).expect("woops")` (dso.rs:300): (median + 3)^2 does not fit a u16
+    g = np.full((40, 40), 300, np.uint16)
+    assert R.dso_select(g, 100, 1, 1) is None and oracle_dso(g, 100, 1, 1)[1] == -1
 
 
 def test_dso_select_deterministic_branches(oracle):
