@@ -103,21 +103,24 @@ def test_partition_covers_every_item_once():
             assert np.array_equal(got, np.arange(n))
 
 
-def test_two_rank_gloo_gather_matches_single_process(oracle):
+@pytest.mark.parametrize("world", [2, 4])
+def test_gloo_gather_matches_single_process(oracle, world):
+    """world 2 (the contract's CPU test) and world 4 (more ranks than some shards have streams: 5 streams over 4 ranks)."""
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = dict(q.get(timeout=240) for _ in range(2))
+    results = dict(q.get(timeout=240) for _ in range(world))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     single = _track_streams(oracle, np.arange(N_STREAMS))
-    assert np.array_equal(results[0], results[1])  # every rank holds the same gathered table
+    for r in range(1, world):
+        assert np.array_equal(results[0], results[r])  # every rank holds the same gathered table
     assert np.array_equal(results[0], single)      # in global stream order, identical to the unsharded run
     assert results[0].shape == (N_STREAMS, 8) and np.all(results[0][:, 7] == 0)
 
